@@ -1,0 +1,237 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference Python code.
+
+Run in the build container only (it needs /root/reference, which does not exist on the GPU
+box):  python tests/golden/make_golden.py
+
+The reference plugin cannot be imported as a package without mmcv/mmdet (its __init__ star-
+imports them), so the two files on the hot path are imported with (a) empty package objects
+pre-seeded in sys.modules and (b) a minimal stand-in for the handful of mmcv symbols they use
+(Linear = nn.Linear, registries, init helpers).  No reference arithmetic is replaced: every
+number stored below is produced by
+  projects/mmdet3d_plugin/ops/__init__.py            (feature_maps_format)
+  projects/mmdet3d_plugin/models/blocks.py           (DeformableFeatureAggregation)
+  projects/mmdet3d_plugin/models/detection3d/blocks.py (SparseBox3DKeyPointsGenerator)
+and torch's grid_sample.  Fixtures are kept small (a few hundred kB in total).
+"""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    def pkg(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [REF + path]
+        sys.modules[name] = m
+
+    for n, p in [("projects", "/projects"), ("projects.mmdet3d_plugin", "/projects/mmdet3d_plugin"),
+                 ("projects.mmdet3d_plugin.core", "/projects/mmdet3d_plugin/core"),
+                 ("projects.mmdet3d_plugin.models", "/projects/mmdet3d_plugin/models"),
+                 ("projects.mmdet3d_plugin.models.detection3d",
+                  "/projects/mmdet3d_plugin/models/detection3d")]:
+        pkg(n, p)
+
+    class Registry:
+        def __init__(self):
+            self.d = {}
+
+        def register_module(self, *a, **k):
+            def deco(c):
+                self.d[c.__name__] = c
+                return c
+            return deco
+
+    def build_from_cfg(cfg, reg, default_args=None):
+        cfg = dict(cfg)
+        return reg.d[cfg.pop("type")](**cfg)
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+
+    class Scale(nn.Module):
+        def __init__(self, scale=1.0):
+            super().__init__()
+            self.scale = nn.Parameter(torch.tensor(scale, dtype=torch.float))
+
+        def forward(self, x):
+            return x * self.scale
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        m.__path__ = []
+        sys.modules[name] = m
+
+    regs = [Registry() for _ in range(4)]
+    mod("mmcv")
+    mod("mmcv.runner")
+    mod("mmcv.cnn.bricks")
+    mod("mmcv.cnn", Linear=nn.Linear, Scale=Scale,
+        build_activation_layer=lambda c: nn.ReLU(inplace=True),
+        build_norm_layer=lambda c, n: (None, nn.LayerNorm(n)),
+        xavier_init=lambda m, distribution="normal", bias=0.0, gain=1: (
+            nn.init.xavier_uniform_(m.weight, gain=gain), nn.init.constant_(m.bias, bias)),
+        constant_init=lambda m, val, bias=0.0: (
+            nn.init.constant_(m.weight, val), nn.init.constant_(m.bias, bias)),
+        bias_init_with_prob=lambda p: float(-np.log((1 - p) / p)))
+    mod("mmcv.runner.base_module", Sequential=nn.Sequential, BaseModule=BaseModule)
+    mod("mmcv.cnn.bricks.transformer", FFN=object)
+    mod("mmcv.utils", build_from_cfg=build_from_cfg)
+    mod("mmcv.cnn.bricks.drop", build_dropout=lambda c: nn.Dropout(c.get("drop_prob", 0.0)))
+    mod("mmcv.cnn.bricks.registry", ATTENTION=regs[0], PLUGIN_LAYERS=regs[1],
+        FEEDFORWARD_NETWORK=regs[2], POSITIONAL_ENCODING=regs[3])
+    blocks = importlib.import_module("projects.mmdet3d_plugin.models.blocks")
+    importlib.import_module("projects.mmdet3d_plugin.models.detection3d.blocks")
+    # feature_maps_format lives in ops/__init__.py, whose first line imports the CUDA
+    # extension wrapper; load the function from the file with that import satisfied by a stub.
+    sys.modules["projects.mmdet3d_plugin.ops.deformable_aggregation"] = types.SimpleNamespace(
+        DeformableAggregationFunction=None)
+    spec = importlib.util.spec_from_file_location(
+        "projects.mmdet3d_plugin.ops", REF + "/projects/mmdet3d_plugin/ops/__init__.py",
+        submodule_search_locations=[])
+    ops = importlib.util.module_from_spec(spec)
+    sys.modules["projects.mmdet3d_plugin.ops"] = ops
+    spec.loader.exec_module(ops)
+    return blocks, ops
+
+
+FIX7 = [[0, 0, 0], [0.45, 0, 0], [-0.45, 0, 0], [0, 0.45, 0], [0, -0.45, 0], [0, 0, 0.45],
+        [0, 0, -0.45]]
+
+
+def make_dfa(blocks, embed, groups, levels, cams, n_learn, fix_scale, camera_embed, residual):
+    return blocks.DeformableFeatureAggregation(
+        embed_dims=embed, num_groups=groups, num_levels=levels, num_cams=cams, attn_drop=0.15,
+        use_deformable_func=False, use_camera_embed=camera_embed, residual_mode=residual,
+        kps_generator=dict(type="SparseBox3DKeyPointsGenerator", num_learnable_pts=n_learn,
+                           fix_scale=fix_scale))
+
+
+def op_case(blocks, name, seed, bs, A, P, K, sizes, C, G, lo, hi, masked, dtype):
+    """Reference fallback (`feature_sampling` + `multi_view_level_fusion` + point sum) on op-level
+    inputs.  The sampling locations are injected through an identity projection:
+    key_points = (x, y, 1), projection_mat = I, image_wh = None  ⇒  points_2d == (x, y)."""
+    g = torch.Generator().manual_seed(seed)
+    maps = [torch.randn(bs, K, C, h, w, generator=g).to(dtype).requires_grad_() for h, w in sizes]
+    loc = (torch.rand(bs, A, P, K, 2, generator=g) * (hi - lo) + lo)
+    # store/compute from the float32 value the op will see
+    loc = loc.float().to(dtype).requires_grad_()
+    logits = torch.randn(bs, A, K * len(sizes) * P, G, generator=g)
+    w_klp = logits.softmax(2).reshape(bs, A, K, len(sizes), P, G).float().to(dtype).requires_grad_()
+    grad_out = torch.randn(bs, A, C, generator=g).float().to(dtype)
+    dfa = make_dfa(blocks, C, G, len(sizes), K, 0, [[0, 0, 0]] * P, False, "add")
+    outs, grads_loc = 0, None
+    # feature_sampling projects ONE set of key points into all cameras; the op takes a separate
+    # location per camera, so evaluate camera by camera (other cameras' weights zeroed).
+    total = 0
+    for k in range(K):
+        kp = torch.cat([loc[:, :, :, k], torch.ones_like(loc[:, :, :, k, :1])], -1)
+        proj = torch.eye(4, dtype=dtype)[None, None].repeat(bs, K, 1, 1)
+        f = blocks.DeformableFeatureAggregation.feature_sampling(maps, kp, proj, None)
+        if masked:
+            x, y = loc[:, :, :, k, 0], loc[:, :, :, k, 1]
+            m = ((x > 0) & (x < 1) & (y > 0) & (y < 1)).to(dtype)          # op mask, .cu:168-171
+            f = f * m[:, :, None, None, :, None]
+        sel = torch.zeros(K, dtype=dtype)
+        sel[k] = 1
+        wk = w_klp * sel[None, None, :, None, None, None]
+        total = total + dfa.multi_view_level_fusion(f, wk).sum(dim=2)
+    total.backward(grad_out)
+    col, shape, start = None, None, None
+    d = dict(loc=loc.detach().float().numpy(),
+             weights=w_klp.detach().permute(0, 1, 4, 2, 3, 5).contiguous().float().numpy(),
+             grad_out=grad_out.float().numpy(), out=total.detach().numpy(),
+             grad_loc=loc.grad.numpy(),
+             grad_weights=w_klp.grad.permute(0, 1, 4, 2, 3, 5).contiguous().numpy(),
+             sizes=np.array(sizes, np.int64), G=np.int64(G), masked=np.int64(masked))
+    for l, m in enumerate(maps):
+        d["map%d" % l] = m.detach().float().numpy()
+        d["grad_map%d" % l] = m.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, "out", total.shape, "abs max", float(total.abs().max()))
+
+
+def flatten_case(ops, name, seed, bs, K, C, sizes):
+    g = torch.Generator().manual_seed(seed)
+    maps = [torch.randn(bs, K, C, h, w, generator=g) for h, w in sizes]
+    col, shape, start = ops.feature_maps_format(maps)
+    back = ops.feature_maps_format([col, shape, start], inverse=True)
+    d = dict(col=col.numpy(), shape=shape.numpy(), start=start.numpy(),
+             sizes=np.array(sizes, np.int64),
+             inverse_n_groups=np.int64(len(back)), inverse_n_levels=np.int64(len(back[0])))
+    for l, m in enumerate(maps):
+        d["map%d" % l] = m.numpy()
+        d["inv%d" % l] = back[0][l].contiguous().numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, col.shape, shape.tolist()[0], start.tolist()[0])
+
+
+def module_case(blocks, name, seed, bs, A, embed, groups, sizes, cams, n_learn, camera_embed,
+                residual):
+    torch.manual_seed(seed)
+    dfa = make_dfa(blocks, embed, groups, len(sizes), cams, n_learn, FIX7, camera_embed, residual)
+    dfa.eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    inst = torch.randn(bs, A, embed, generator=g)
+    emb = torch.randn(bs, A, embed, generator=g)
+    anchor = torch.randn(bs, A, 11, generator=g)
+    anchor[..., :2] *= 8.0
+    anchor[..., 3:6] *= 0.3
+    maps = [torch.randn(bs, cams, embed, h, w, generator=g) for h, w in sizes]
+    # toy pinhole cameras looking along +y / -y / +x, 64x32 image
+    proj = torch.zeros(bs, cams, 4, 4)
+    for k in range(cams):
+        a = 2 * np.pi * k / cams
+        fwd = np.array([-np.sin(a), np.cos(a), 0.0])
+        right = np.array([np.cos(a), np.sin(a), 0.0])
+        down = np.array([0.0, 0.0, -1.0])
+        E = np.eye(4)
+        E[:3, :3] = np.stack([right, down, fwd])
+        Km = np.eye(4)
+        Km[0, 0] = Km[1, 1] = 30.0
+        Km[0, 2], Km[1, 2] = 32.0, 16.0
+        proj[:, k] = torch.tensor(Km @ E, dtype=torch.float32)
+    wh = torch.tensor([64.0, 32.0])[None, None].repeat(bs, cams, 1)
+    metas = dict(projection_mat=proj, image_wh=wh)
+    with torch.no_grad():
+        out = dfa(inst, anchor, emb, maps, metas)
+        kp = dfa.kps_generator(anchor, inst)
+        w = dfa._get_weights(inst, emb, metas)
+        uv = dfa.project_points(kp, proj, wh)
+    d = dict(instance_feature=inst.numpy(), anchor_embed=emb.numpy(), anchor=anchor.numpy(),
+             projection_mat=proj.numpy(), image_wh=wh.numpy(), out=out.numpy(),
+             key_points=kp.numpy(), weights=w.numpy(), points_2d=uv.numpy(),
+             sizes=np.array(sizes, np.int64),
+             cfg=np.array([embed, groups, len(sizes), cams, n_learn, int(camera_embed),
+                           int(residual == "cat")], np.int64))
+    for l, m in enumerate(maps):
+        d["map%d" % l] = m.numpy()
+    for k, v in dfa.state_dict().items():
+        d["sd." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, out.shape, sorted(dfa.state_dict().keys()))
+
+
+if __name__ == "__main__":
+    blocks, ops = import_reference()
+    sizes = [(8, 12), (4, 6), (2, 3)]
+    flatten_case(ops, "flatten_small", 1, bs=2, K=3, C=16, sizes=sizes)
+    # op vs reference fallback with the op's mask multiplied in, fp64 + fp32
+    op_case(blocks, "op_masked_f64", 2, 2, 7, 5, 3, sizes, 32, 4, -0.15, 1.15, True, torch.float64)
+    op_case(blocks, "op_masked_f32", 3, 2, 7, 5, 3, sizes, 32, 4, -0.15, 1.15, True, torch.float32)
+    # unmasked fallback on inputs that stay clear of the half-pixel border band
+    op_case(blocks, "op_inner_f64", 4, 1, 9, 4, 2, sizes, 64, 8, 0.26, 0.74, False, torch.float64)
+    module_case(blocks, "module_cat_cam", 5, bs=2, A=11, embed=64, groups=4, sizes=sizes, cams=3,
+                n_learn=2, camera_embed=True, residual="cat")
+    module_case(blocks, "module_add_nocam", 6, bs=1, A=6, embed=32, groups=2, sizes=sizes, cams=2,
+                n_learn=0, camera_embed=False, residual="add")
