@@ -1,0 +1,122 @@
+/*
+ * dfa_b200.h — C ABI of libdfa_b200.so: SimPB's deformable feature aggregation hot path,
+ * hand-written CUDA for sm_100a (B200).
+ *
+ * This is the drop-in boundary.  Every entry point takes plain pointers and sizes (device
+ * pointers unless the name ends in `_host`), an explicit CUDA stream, and returns an int:
+ *   0                      success
+ *   > 0                    a cudaError_t raised by the launch / runtime
+ *   DFA_ERR_* (< 0)        argument validation failed — nothing was launched
+ * Nothing throws across this boundary and the library keeps no global state, so it is
+ * re-entrant from any host thread (PyTorch's autograd thread included).
+ *
+ * Reference interface each entry point replaces (paths under
+ * /root/reference/projects/mmdet3d_plugin/):
+ *   dfa_forward            ops/src/deformable_aggregation_cuda.cu:265-288  (deformable_aggregation)
+ *   dfa_backward           ops/src/deformable_aggregation_cuda.cu:291-318  (deformable_aggregation_grad)
+ *   dfa_flatten_maps       ops/__init__.py:63-92                           (feature_maps_format)
+ *   dfa_keypoints_project  models/detection3d/blocks.py:181-207 + models/blocks.py:198-213
+ *   dfa_forward_host       the same forward, called with HOST buffers (copies inside)
+ *
+ * Tensor layouts (row-major, innermost last) — ops/src/deformable_aggregation.cpp:22-28:
+ *   mc_ms_feat         [bs, num_feat, C]         float32 or bfloat16 (feat_dtype)
+ *   spatial_shape      [K, L, 2]  = (H, W)       int32
+ *   scale_start_index  [K, L]                    int32, first row of (camera k, level l)
+ *   sampling_location  [bs, A, P, K, 2] = (x, y) float32, normalised to the image
+ *   weights            [bs, A, P, K, L, G]       float32
+ *   output             [bs, A, C]                float32
+ */
+#ifndef DFA_B200_H_
+#define DFA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFA_B200_VERSION 100
+
+/* argument-validation errors (negative so they never collide with cudaError_t) */
+#define DFA_ERR_NULL_POINTER (-1)
+#define DFA_ERR_BAD_DIMS (-2)        /* non-positive dim, C % G != 0, int32 index overflow */
+#define DFA_ERR_BAD_DTYPE (-3)
+#define DFA_ERR_MISALIGNED (-4)      /* a pointer is not aligned for its element type */
+#define DFA_ERR_UNSUPPORTED (-5)
+
+/* feature element types */
+#define DFA_F32 0
+#define DFA_BF16 1
+
+/* dfa_backward flags */
+#define DFA_BWD_ACCUMULATE 0      /* reference contract: add into caller-zeroed gradient buffers  */
+#define DFA_BWD_OVERWRITE_SMALL 1 /* grad_sampling_location / grad_weights are fully written
+                                     (zeros for masked samples): no memset needed for them     */
+#define DFA_BWD_ZERO_GRAD_FEAT 2  /* the library zero-fills grad_mc_ms_feat on `stream` first     */
+
+/* Same eight sizes the reference launchers take (…_cuda.cu:272-279), in the same order. */
+typedef struct dfa_dims {
+  int32_t batch_size;  /* bs */
+  int32_t num_cams;    /* K  */
+  int32_t num_feat;    /* rows of mc_ms_feat per batch item */
+  int32_t num_embeds;  /* C  */
+  int32_t num_scale;   /* L  */
+  int32_t num_anchors; /* A  */
+  int32_t num_pts;     /* P  */
+  int32_t num_groups;  /* G  */
+} dfa_dims;
+
+int dfa_version(void);
+const char *dfa_error_string(int code);
+
+/* out[b,a,c] = sum_{p,k,l} valid(b,a,p,k) * w[b,a,p,k,l,c/(C/G)] * bilinear(feat, loc)  —
+ * `output` is written, not accumulated: it needs no zero-fill (the reference needs at::zeros,
+ * deformable_aggregation.cpp:55). */
+int dfa_forward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_shape,
+                const int32_t *scale_start_index, const float *sampling_location,
+                const float *weights, float *output, const dfa_dims *dims, void *stream);
+
+/* Gradients wrt features, sampling locations and weights.  grad_mc_ms_feat is float32
+ * [bs,num_feat,C] whatever feat_dtype is, and is always accumulated into (scatter). */
+int dfa_backward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_shape,
+                 const int32_t *scale_start_index, const float *sampling_location,
+                 const float *weights, const float *grad_output, float *grad_mc_ms_feat,
+                 float *grad_sampling_location, float *grad_weights, const dfa_dims *dims,
+                 int flags, void *stream);
+
+/* Test side channel: the geometry the kernels use, for the bit-exact checks.
+ * valid [bs,A,P,K] uint8; corner_rows [bs,A,P,K,L,4] int32 (row in [0,num_feat) or -1). */
+int dfa_debug_indices(const int32_t *spatial_shape, const int32_t *scale_start_index,
+                      const float *sampling_location, uint8_t *valid, int32_t *corner_rows,
+                      const dfa_dims *dims, void *stream);
+
+/* Flatten L feature maps [bs, K, C, H_l, W_l] (NCHW, float32) into the multi-camera /
+ * multi-scale channel-last layout [bs, K*sum(H_l*W_l), C] in one pass; out_dtype selects
+ * float32 or bfloat16 output.  level_ptrs / level_hw are HOST arrays (L pointers, L (H,W)). */
+int dfa_flatten_maps(const float *const *level_ptrs, const int32_t *level_hw, int num_levels,
+                     int bs, int num_cams, int channels, void *col_feats, int out_dtype,
+                     void *stream);
+
+/* Key-point generation + camera projection:
+ *   anchor [bs,A,11], fix_scale [F,3], learnable_logits [bs,A,(P-F)*3] or NULL (then P == F),
+ *   projection_mat [bs,K,4,4], image_wh [bs,K,2] or NULL
+ *   → key_points [bs,A,P,3] (may be NULL) and sampling_location [bs,A,P,K,2]. */
+int dfa_keypoints_project(const float *anchor, const float *fix_scale, int num_fix,
+                          const float *learnable_logits, const float *projection_mat,
+                          const float *image_wh, float *key_points, float *sampling_location,
+                          int bs, int num_anchors, int num_pts, int num_cams, void *stream);
+
+/* Forward with HOST buffers: host→device copies of all five inputs, the kernel, and the
+ * device→host copy of the output, on `stream`, then a stream synchronise.  Host buffers should
+ * be pinned for the copies to be asynchronous.  `workspace` is a device buffer of at least
+ * dfa_forward_host_workspace_bytes() bytes (the library never allocates). */
+int64_t dfa_forward_host_workspace_bytes(int feat_dtype, const dfa_dims *dims);
+int dfa_forward_host(const void *h_mc_ms_feat, int feat_dtype, const int32_t *h_spatial_shape,
+                     const int32_t *h_scale_start_index, const float *h_sampling_location,
+                     const float *h_weights, float *h_output, const dfa_dims *dims,
+                     void *workspace, int64_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFA_B200_H_ */

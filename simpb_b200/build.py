@@ -1,0 +1,77 @@
+"""In-tree build of the native code (sm_100a only).
+
+  libdfa_b200.so                          CUDA kernels + the C ABI of include/dfa_b200.h (nvcc)
+  ops/deformable_aggregation_ext*.so      thin torch extension with the reference's two entry
+                                          points, forwarding raw pointers to the C ABI (g++)
+
+Both land next to the sources so they travel with the repository snapshot to the GPU box.
+"""
+import os
+import subprocess
+import sys
+import sysconfig
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB = os.path.join(PKG, "libdfa_b200.so")
+KERNEL_SRC = os.path.join(PKG, "csrc", "dfa_kernels.cu")
+EXT_SRC = os.path.join(PKG, "csrc", "dfa_torch_ext.cpp")
+HEADER = os.path.join(ROOT, "include", "dfa_b200.h")
+EXT = os.path.join(PKG, "ops", "deformable_aggregation_ext" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]
+
+
+def _stale(target, sources):
+    return (not os.path.exists(target)
+            or any(os.path.getmtime(target) < os.path.getmtime(s) for s in sources))
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s%s" % (" ".join(cmd), r.stdout[-4000:], r.stderr[-4000:]))
+    return r
+
+
+def build_lib(force=False, verbose=False):
+    if force or _stale(LIB, [KERNEL_SRC, HEADER]):
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB, KERNEL_SRC]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = _run(cmd)
+        if verbose:
+            print(r.stderr, file=sys.stderr)
+    return LIB
+
+
+def build_ext(force=False):
+    """The extension holds no device code: it validates tensors, takes PyTorch's current stream
+    and calls libdfa_b200.so (found through an $ORIGIN rpath)."""
+    build_lib(force)
+    if force or _stale(EXT, [EXT_SRC, HEADER, LIB]):
+        import torch
+        from torch.utils import cpp_extension as ce
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", EXT_SRC, "-o", EXT,
+               "-DTORCH_EXTENSION_NAME=deformable_aggregation_ext", "-DTORCH_API_INCLUDE_EXTENSION_H",
+               "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+               "-I", os.path.join(ROOT, "include")]
+        for p in ce.include_paths("cuda") + [sysconfig.get_paths()["include"]]:
+            cmd += ["-isystem", p]
+        for d in ce.library_paths("cuda"):
+            cmd += ["-L" + d, "-Wl,-rpath," + d]
+        cmd += ["-L" + PKG, "-Wl,-rpath,$ORIGIN/..", "-ldfa_b200", "-lc10", "-lc10_cuda",
+                "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python", "-lcudart"]
+        _run(cmd)
+    return EXT
+
+
+def build_all(force=False, verbose=False):
+    build_lib(force, verbose)
+    build_ext(force)
+    return LIB, EXT
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,244 @@
+"""ctypes binding of libdfa_b200.so (the C ABI declared in include/dfa_b200.h).
+
+This is the host side of the product path: PyTorch supplies device memory and the current
+stream, the library does the work.  There is no fallback: if the shared library is missing the
+import raises, and every non-zero return code raises `DfaError`.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdfa_b200.so")
+
+F32, BF16 = 0, 1
+BWD_ACCUMULATE, BWD_OVERWRITE_SMALL, BWD_ZERO_GRAD_FEAT = 0, 1, 2
+
+# every symbol include/dfa_b200.h declares (tests check the library exports each of them)
+SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_forward", "dfa_backward", "dfa_debug_indices",
+           "dfa_flatten_maps", "dfa_keypoints_project", "dfa_forward_host_workspace_bytes",
+           "dfa_forward_host")
+
+
+class DfaError(RuntimeError):
+    pass
+
+
+class Dims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch_size", "num_cams", "num_feat", "num_embeds",
+                                              "num_scale", "num_anchors", "num_pts", "num_groups")]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not found — build it with `python -m simpb_b200.build` "
+                          "(the CUDA path has no fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    dp = ctypes.POINTER(Dims)
+    lib.dfa_version.restype = i32
+    lib.dfa_error_string.restype = ctypes.c_char_p
+    lib.dfa_error_string.argtypes = [i32]
+    lib.dfa_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp]
+    lib.dfa_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, dp, i32, vp]
+    lib.dfa_debug_indices.argtypes = [vp, vp, vp, vp, vp, dp, vp]
+    lib.dfa_flatten_maps.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp]
+    lib.dfa_keypoints_project.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.dfa_forward_host_workspace_bytes.restype = i64
+    lib.dfa_forward_host_workspace_bytes.argtypes = [i32, dp]
+    lib.dfa_forward_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp, i64, vp]
+    for name in ("dfa_forward", "dfa_backward", "dfa_debug_indices", "dfa_flatten_maps",
+                 "dfa_keypoints_project", "dfa_forward_host"):
+        getattr(lib, name).restype = i32
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    if rc != 0:
+        raise DfaError("%s failed: %s (code %d)" % (what, lib.dfa_error_string(rc).decode(), rc))
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def feat_dtype(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise DfaError("mc_ms_feat must be float32 or bfloat16, got %s" % t.dtype)
+
+
+def _need(t, name, dtype=None, cuda=True):
+    if not isinstance(t, torch.Tensor):
+        raise DfaError("%s must be a tensor" % name)
+    if cuda and not t.is_cuda:
+        raise DfaError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if not t.is_contiguous():
+        raise DfaError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise DfaError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def op_dims(feat, shape, start, loc, w):
+    """Same size extraction as deformable_aggregation.cpp:40-47, plus the shape checks the
+    reference omits."""
+    if feat.dim() != 3 or shape.dim() != 3 or shape.shape[2] != 2 or start.dim() != 2 \
+            or loc.dim() != 5 or loc.shape[4] != 2 or w.dim() != 6:
+        raise DfaError("deformable_aggregation: wrong tensor ranks")
+    bs, num_feat, C = feat.shape
+    K, L = shape.shape[:2]
+    A, P = loc.shape[1:3]
+    G = w.shape[5]
+    if tuple(start.shape) != (K, L) or tuple(loc.shape) != (bs, A, P, K, 2) \
+            or tuple(w.shape) != (bs, A, P, K, L, G):
+        raise DfaError("deformable_aggregation: inconsistent shapes feat=%s shape=%s start=%s "
+                       "loc=%s weights=%s" % (tuple(feat.shape), tuple(shape.shape),
+                                              tuple(start.shape), tuple(loc.shape), tuple(w.shape)))
+    return Dims(bs, K, num_feat, C, L, A, P, G)
+
+
+def forward(feat, shape, start, loc, w, out=None):
+    _need(feat, "mc_ms_feat"); _need(shape, "spatial_shape", torch.int32)
+    _need(start, "scale_start_index", torch.int32)
+    _need(loc, "sampling_location", torch.float32); _need(w, "weights", torch.float32)
+    d = op_dims(feat, shape, start, loc, w)
+    if out is None:
+        out = torch.empty(d.batch_size, d.num_anchors, d.num_embeds, device=feat.device,
+                          dtype=torch.float32)
+    with torch.cuda.device(feat.device):
+        check(lib.dfa_forward(feat.data_ptr(), feat_dtype(feat), shape.data_ptr(), start.data_ptr(),
+                              loc.data_ptr(), w.data_ptr(), out.data_ptr(), ctypes.byref(d),
+                              stream_ptr(feat.device)), "dfa_forward")
+    return out
+
+
+def backward(feat, shape, start, loc, w, grad_out, grad_feat=None, grad_loc=None, grad_w=None,
+             flags=None):
+    """With no buffers given: allocates them, lets the kernel write the two small gradients in full
+    and zero-fills grad_feat on the stream (one memset instead of the reference's three)."""
+    _need(feat, "mc_ms_feat"); _need(shape, "spatial_shape", torch.int32)
+    _need(start, "scale_start_index", torch.int32)
+    _need(loc, "sampling_location", torch.float32); _need(w, "weights", torch.float32)
+    _need(grad_out, "grad_output", torch.float32)
+    d = op_dims(feat, shape, start, loc, w)
+    if tuple(grad_out.shape) != (d.batch_size, d.num_anchors, d.num_embeds):
+        raise DfaError("grad_output must be [bs, anchors, embeds]")
+    if flags is None:
+        flags = BWD_ACCUMULATE if (grad_feat is not None and grad_loc is not None
+                                   and grad_w is not None) else None
+    if flags is None:
+        flags = BWD_OVERWRITE_SMALL
+        if grad_feat is None:
+            grad_feat = torch.empty(feat.shape, device=feat.device, dtype=torch.float32)
+            flags |= BWD_ZERO_GRAD_FEAT
+        grad_loc = torch.empty_like(loc) if grad_loc is None else grad_loc
+        grad_w = torch.empty_like(w) if grad_w is None else grad_w
+    for t, n in ((grad_feat, "grad_mc_ms_feat"), (grad_loc, "grad_sampling_location"),
+                 (grad_w, "grad_weights")):
+        _need(t, n, torch.float32)
+    if grad_feat.numel() != feat.numel() or grad_loc.numel() != loc.numel() \
+            or grad_w.numel() != w.numel():
+        raise DfaError("gradient buffer sizes do not match their inputs")
+    with torch.cuda.device(feat.device):
+        check(lib.dfa_backward(feat.data_ptr(), feat_dtype(feat), shape.data_ptr(), start.data_ptr(),
+                               loc.data_ptr(), w.data_ptr(), grad_out.data_ptr(),
+                               grad_feat.data_ptr(), grad_loc.data_ptr(), grad_w.data_ptr(),
+                               ctypes.byref(d), int(flags), stream_ptr(feat.device)), "dfa_backward")
+    return grad_feat, grad_loc, grad_w
+
+
+def debug_indices(shape, start, loc):
+    _need(shape, "spatial_shape", torch.int32); _need(start, "scale_start_index", torch.int32)
+    _need(loc, "sampling_location", torch.float32)
+    bs, A, P, K, _ = loc.shape
+    L = shape.shape[1]
+    d = Dims(bs, K, 1, 1, L, A, P, 1)
+    valid = torch.empty(bs, A, P, K, device=loc.device, dtype=torch.uint8)
+    rows = torch.empty(bs, A, P, K, L, 4, device=loc.device, dtype=torch.int32)
+    with torch.cuda.device(loc.device):
+        check(lib.dfa_debug_indices(shape.data_ptr(), start.data_ptr(), loc.data_ptr(),
+                                    valid.data_ptr(), rows.data_ptr(), ctypes.byref(d),
+                                    stream_ptr(loc.device)), "dfa_debug_indices")
+    return valid, rows
+
+
+def flatten_maps(maps, out_dtype=torch.float32, out=None):
+    """maps: list over levels of contiguous float32 CUDA tensors [bs, K, C, H_l, W_l]."""
+    L = len(maps)
+    bs, K, C = maps[0].shape[:3]
+    for m in maps:
+        _need(m, "feature map", torch.float32)
+        if m.dim() != 5 or tuple(m.shape[:3]) != (bs, K, C):
+            raise DfaError("feature maps must all be [bs, cams, C, H_l, W_l]")
+    rows = K * sum(int(m.shape[3]) * int(m.shape[4]) for m in maps)
+    if out is None:
+        out = torch.empty(bs, rows, C, device=maps[0].device, dtype=out_dtype)
+    ptrs = (ctypes.c_void_p * L)(*[m.data_ptr() for m in maps])
+    hw = (ctypes.c_int32 * (2 * L))(*[int(v) for m in maps for v in m.shape[3:5]])
+    with torch.cuda.device(out.device):
+        check(lib.dfa_flatten_maps(ptrs, hw, L, bs, K, C, out.data_ptr(), feat_dtype(out),
+                                   stream_ptr(out.device)), "dfa_flatten_maps")
+    return out
+
+
+def keypoints_project(anchor, fix_scale, learnable_logits, projection_mat, image_wh,
+                      want_key_points=False):
+    _need(anchor, "anchor", torch.float32); _need(fix_scale, "fix_scale", torch.float32)
+    _need(projection_mat, "projection_mat", torch.float32)
+    bs, A = anchor.shape[:2]
+    if anchor.shape[2] != 11:
+        raise DfaError("anchor must be [bs, A, 11]")
+    F_ = fix_scale.shape[0]
+    n_learn = 0
+    if learnable_logits is not None:
+        _need(learnable_logits, "learnable_logits", torch.float32)
+        n_learn = learnable_logits.numel() // (bs * A * 3)
+    P, K = F_ + n_learn, projection_mat.shape[1]
+    if image_wh is not None:
+        _need(image_wh, "image_wh", torch.float32)
+    kp = torch.empty(bs, A, P, 3, device=anchor.device) if want_key_points else None
+    loc = torch.empty(bs, A, P, K, 2, device=anchor.device)
+    with torch.cuda.device(anchor.device):
+        check(lib.dfa_keypoints_project(
+            anchor.data_ptr(), fix_scale.data_ptr(), F_,
+            learnable_logits.data_ptr() if learnable_logits is not None else None,
+            projection_mat.data_ptr(), image_wh.data_ptr() if image_wh is not None else None,
+            kp.data_ptr() if kp is not None else None, loc.data_ptr(), bs, A, P, K,
+            stream_ptr(anchor.device)), "dfa_keypoints_project")
+    return (loc, kp) if want_key_points else loc
+
+
+class HostForward:
+    """End-to-end forward with HOST (pinned) buffers through dfa_forward_host: host→device copies,
+    the kernel and the device→host copy of the result all happen inside the call."""
+
+    def __init__(self, dims, dtype=torch.float32, device="cuda"):
+        self.dims = dims
+        self.dt = F32 if dtype == torch.float32 else BF16
+        n = lib.dfa_forward_host_workspace_bytes(self.dt, ctypes.byref(dims))
+        if n < 0:
+            raise DfaError("bad dims for dfa_forward_host")
+        self.nbytes = int(n)
+        self.workspace = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.device = self.workspace.device
+
+    def __call__(self, h_feat, h_shape, h_start, h_loc, h_w, h_out):
+        for t, n in ((h_feat, "feat"), (h_shape, "shape"), (h_start, "start"), (h_loc, "loc"),
+                     (h_w, "weights"), (h_out, "out")):
+            _need(t, n, cuda=False)
+            if t.is_cuda:
+                raise DfaError("dfa_forward_host takes host tensors")
+        with torch.cuda.device(self.device):
+            check(lib.dfa_forward_host(h_feat.data_ptr(), self.dt, h_shape.data_ptr(),
+                                       h_start.data_ptr(), h_loc.data_ptr(), h_w.data_ptr(),
+                                       h_out.data_ptr(), ctypes.byref(self.dims),
+                                       self.workspace.data_ptr(), self.nbytes,
+                                       stream_ptr(self.device)), "dfa_forward_host")
+        return h_out

@@ -1,0 +1,1006 @@
+// dfa_kernels.cu — deformable feature aggregation for SimPB, hand-written for sm_100a (B200).
+//
+// One CTA owns one anchor (b, a).  Its sampling locations (P*K*2 floats) and weights
+// (P*K*L*G floats) are contiguous per anchor and are staged into shared memory with two
+// TMA bulk copies (cp.async.bulk → UBLKCP) completing on mbarriers.  Warp 0 compacts the
+// samples that pass the op's exclusive (0,1) test; the CTA then builds one 32-byte "tap"
+// record per (valid sample, level): the four corner element offsets and bilinear weights.
+// In the main loop warp g owns channel group g: its lanes are split as
+//     lane = [sub-tap s][corner q][16-byte vector j]
+// so one 128-bit load per lane fetches the group's contiguous channels of all four corners
+// (fp32: 8 lanes x 16 B = the group's 128 B per corner).  The weighted sum lives in
+// registers; corners are folded with two warp shuffles at the end and the anchor's output row
+// is written once with plain vector stores — no atomics and no zero-filled output.
+//
+// The backward keeps the same ownership: grad_weights[b,a,p,k,l,g] is produced by exactly one
+// warp (shuffle reduction, plain store) and grad_sampling_location[b,a,p,k,:] by exactly one
+// CTA (per-warp shared-memory rows, summed in a fixed order).  Only grad_mc_ms_feat, where
+// different anchors meet on the same pixel, is scattered — with 128-bit vector reductions
+// (red.global.add.v4.f32).
+//
+// Semantics follow /root/reference/projects/mmdet3d_plugin/ops/src/deformable_aggregation_cuda.cu
+// (forward :129-187 + :13-59, backward :190-262 + :62-126); the pixel coordinate uses the single
+// fused multiply-add the compiled reference uses (SURVEY.md §7 "bit-exact indices").
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dfa_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// small PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global → shared, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry shared by every kernel (and by the debug side channel the parity tests read)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sample_valid(float x, float y) {
+  // …_cuda.cu:168-171: `if (loc <= 0 || loc >= 1) return;` — exclusive on both ends
+  return !(x <= 0.f || x >= 1.f) && !(y <= 0.f || y >= 1.f);
+}
+
+struct TapGeom {
+  int row[4];  // row inside the batch item's feature table, -1 when the corner is outside
+  float lh, lw, hh, hw;
+};
+
+__device__ __forceinline__ void tap_geometry(float x, float y, int H, int W, int start, TapGeom &g) {
+  // …_cuda.cu:180-181 as compiled: one FFMA(loc, size, -0.5), then floor (:18-25)
+  const float h_im = fmaf(y, static_cast<float>(H), -0.5f);
+  const float w_im = fmaf(x, static_cast<float>(W), -0.5f);
+  const float fh = floorf(h_im), fw = floorf(w_im);
+  const int h_low = static_cast<int>(fh), w_low = static_cast<int>(fw);
+  g.lh = h_im - fh;
+  g.lw = w_im - fw;
+  g.hh = 1.f - g.lh;
+  g.hw = 1.f - g.lw;
+  const bool hl = h_low >= 0, wl = w_low >= 0;            // :33, :38, :43, :48
+  const bool hh = h_low + 1 <= H - 1, wh = w_low + 1 <= W - 1;
+  const int base = start + h_low * W + w_low;
+  g.row[0] = (hl && wl) ? base : -1;
+  g.row[1] = (hl && wh) ? base + 1 : -1;
+  g.row[2] = (hh && wl) ? base + W : -1;
+  g.row[3] = (hh && wh) ? base + W + 1 : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// feature vector access: one 16-byte load = VEC channels
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct FeatVec;
+template <>
+struct FeatVec<float> {
+  static constexpr int VEC = 4;
+  __device__ static __forceinline__ void load(const float *p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+};
+template <>
+struct FeatVec<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bf16 → fp32 is a 16-bit shift
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+
+struct Dims {
+  int bs, K, num_feat, C, L, A, P, G;
+};
+
+// shared-memory carve-up, identical on host and device
+struct SmemLayout {
+  uint32_t w, loc, rec, widx, list, gl, bar, total;
+};
+__host__ __device__ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ inline SmemLayout smem_layout(int P, int K, int L, int G, int tap_pad,
+                                                  bool backward) {
+  SmemLayout s;
+  const uint32_t taps = align_up(static_cast<uint32_t>(P) * K * L, tap_pad) + tap_pad;
+  uint32_t o = 0;
+  s.w = o, o = align_up(o + 4u * P * K * L * G, 16);
+  s.loc = o, o = align_up(o + 8u * P * K, 16);
+  s.rec = o, o = align_up(o + 32u * taps, 16);
+  s.widx = o, o = align_up(o + 4u * taps, 16);
+  s.list = o, o = align_up(o + 4u * P * K, 16);
+  s.gl = o, o = align_up(o + (backward ? 8u * P * K * G : 0u), 16);
+  s.bar = o, o += 32;
+  s.total = o;
+  return s;
+}
+
+struct TapQ {  // forward record, one per corner
+  int off;     // element offset of the corner's row inside the batch item, -1 = skip
+  float bw;    // bilinear weight
+};
+struct TapB {  // backward record, one per tap
+  int off[4];
+  float lh, lw, Wf, Hf;
+};
+
+// Stage the anchor's locations and weights, compact valid samples.  Returns n_valid.
+template <bool TMA>
+__device__ __forceinline__ int stage_and_compact(const float *__restrict__ loc_g,
+                                                 const float *__restrict__ w_g, float *s_w,
+                                                 float *s_loc, int *s_list, uint64_t *bars,
+                                                 int *s_nvalid, int PK, int wcount) {
+  const int tid = threadIdx.x;
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      fence_mbar_init();
+      mbar_expect_tx(&bars[0], 8u * PK);
+      tma_bulk_g2s(s_loc, loc_g, 8u * PK, &bars[0]);
+      mbar_expect_tx(&bars[1], 4u * wcount);
+      tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
+    }
+    __syncthreads();  // barrier init visible to every waiter
+    if (tid < 32) mbar_wait(&bars[0], 0);
+  } else {
+    for (int i = tid; i < 2 * PK; i += blockDim.x) s_loc[i] = __ldg(loc_g + i);
+    for (int i = tid; i < wcount; i += blockDim.x) s_w[i] = __ldg(w_g + i);
+    __syncthreads();
+  }
+  if (tid < 32) {
+    int n = 0;
+    for (int base = 0; base < PK; base += 32) {
+      const int s = base + tid;
+      bool v = false;
+      if (s < PK) v = sample_valid(s_loc[2 * s], s_loc[2 * s + 1]);
+      const unsigned m = __ballot_sync(0xffffffffu, v);
+      if (v) s_list[n + __popc(m & ((1u << tid) - 1u))] = s;
+      n += __popc(m);
+    }
+    if (tid == 0) *s_nvalid = n;
+  }
+  __syncthreads();
+  return *s_nvalid;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+// T: feature element type.  LPG: lanes per group row = (C/G)*sizeof(T)/16.  U: taps in flight
+// per lane.  Block = 32*G threads (warp g = group g).
+template <typename T, int LPG, int U, bool TMA, int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256) ? ((sizeof(T) == 4 ? 1536 : 1024) / MAXT) : 1)
+    dfa_fwd_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                   const int *__restrict__ start, const float *__restrict__ loc,
+                   const float *__restrict__ weights, float *__restrict__ out, Dims d) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  constexpr int TPW = 32 / (4 * LPG);  // taps one warp instruction covers
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, TPW * U, false);
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  TapQ *s_rec = reinterpret_cast<TapQ *>(smem + lay.rec);
+  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  int *s_list = reinterpret_cast<int *>(smem + lay.list);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int anchor = blockIdx.x;  // b * A + a
+  const int b = anchor / d.A;
+  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
+
+  const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
+                                        weights + static_cast<size_t>(anchor) * wcount, s_w,
+                                        s_loc, s_list, bars, s_nvalid, PK, wcount);
+  const int ntaps = nv * d.L;
+  const int ntaps_pad = (ntaps + TPW * U - 1) / (TPW * U) * (TPW * U);
+
+  // tap records, level-major so that the coarse levels' shared rows are touched back to back
+  for (int t = tid; t < ntaps_pad; t += blockDim.x) {
+    TapQ r[4] = {{-1, 0.f}, {-1, 0.f}, {-1, 0.f}, {-1, 0.f}};
+    int widx = 0;
+    if (t < ntaps) {
+      const int l = t / nv, i = t - l * nv;
+      const int s = s_list[i];
+      const int k = s % d.K;
+      const int kl = k * d.L + l;
+      const int H = __ldg(shape + 2 * kl), W = __ldg(shape + 2 * kl + 1);
+      TapGeom gm;
+      tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], H, W, __ldg(start + kl), gm);
+      const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (gm.row[q] >= 0) r[q].off = gm.row[q] * d.C, r[q].bw = bw[q];
+      widx = (s * d.L + l) * d.G;
+    }
+    int4 *dst = reinterpret_cast<int4 *>(s_rec + 4 * t);
+    dst[0] = make_int4(r[0].off, __float_as_int(r[0].bw), r[1].off, __float_as_int(r[1].bw));
+    dst[1] = make_int4(r[2].off, __float_as_int(r[2].bw), r[3].off, __float_as_int(r[3].bw));
+    s_widx[t] = widx;
+  }
+  __syncthreads();
+  if (TMA) mbar_wait(&bars[1], 0);  // weights have landed
+
+  const int j = lane % LPG, q = (lane / LPG) & 3, sub = lane / (4 * LPG);
+  const int cpg = d.C / d.G;
+  const T *fb = feat + static_cast<size_t>(b) * d.num_feat * d.C + g * cpg + j * VEC;
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+
+  for (int t0 = 0; t0 < ntaps_pad; t0 += TPW * U) {
+    float v[U][VEC], cw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * TPW + sub;
+      const int2 rq = *reinterpret_cast<const int2 *>(s_rec + 4 * t + q);
+      const float wgt = s_w[s_widx[t] + g];
+      if (rq.x >= 0) {
+        cw[u] = __int_as_float(rq.y) * wgt;
+        FeatVec<T>::load(fb + rq.x, v[u]);
+      } else {  // corner outside the map (zero padding) or padding tap: contributes nothing
+        cw[u] = 0.f;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) v[u][c] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) acc[c] = fmaf(cw[u], v[u][c], acc[c]);
+  }
+  // fold corners (and sub-taps): lanes differing in bits >= log2(LPG)
+#pragma unroll
+  for (int m = LPG; m < 32; m <<= 1)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], m);
+  if (lane < LPG) {
+    float4 *o = reinterpret_cast<float4 *>(out + static_cast<size_t>(anchor) * d.C + g * cpg + j * VEC);
+#pragma unroll
+    for (int c = 0; c < VEC / 4; ++c)
+      o[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+  }
+}
+
+// Shape-generic forward (any C, G with C % G == 0, any alignment): one CTA per anchor, threads
+// stride over channels, scalar loads.  Same staging/geometry code, no atomics.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    dfa_fwd_generic_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                           const int *__restrict__ start, const float *__restrict__ loc,
+                           const float *__restrict__ weights, float *__restrict__ out, Dims d) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, 1, false);
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  TapQ *s_rec = reinterpret_cast<TapQ *>(smem + lay.rec);
+  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  int *s_list = reinterpret_cast<int *>(smem + lay.list);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+  const int tid = threadIdx.x, anchor = blockIdx.x, b = anchor / d.A;
+  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
+  const int nv = stage_and_compact<false>(loc + static_cast<size_t>(anchor) * PK * 2,
+                                          weights + static_cast<size_t>(anchor) * wcount, s_w,
+                                          s_loc, s_list, bars, s_nvalid, PK, wcount);
+  const int ntaps = nv * d.L;
+  for (int t = tid; t < ntaps; t += blockDim.x) {
+    const int l = t / nv, i = t - l * nv, s = s_list[i], k = s % d.K, kl = k * d.L + l;
+    const int H = __ldg(shape + 2 * kl), W = __ldg(shape + 2 * kl + 1);
+    TapGeom gm;
+    tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], H, W, __ldg(start + kl), gm);
+    const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
+    for (int q = 0; q < 4; ++q) {
+      s_rec[4 * t + q].off = gm.row[q] >= 0 ? gm.row[q] * d.C : -1;
+      s_rec[4 * t + q].bw = gm.row[q] >= 0 ? bw[q] : 0.f;
+    }
+    s_widx[t] = (s * d.L + l) * d.G;
+  }
+  __syncthreads();
+  const int cpg = d.C / d.G;
+  const T *fb = feat + static_cast<size_t>(b) * d.num_feat * d.C;
+  for (int c = tid; c < d.C; c += blockDim.x) {
+    const int grp = c / cpg;
+    float acc = 0.f;
+    for (int t = 0; t < ntaps; ++t) {
+      const float wgt = s_w[s_widx[t] + grp];
+      float val = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const TapQ r = s_rec[4 * t + q];
+        if (r.off >= 0) val = fmaf(r.bw, static_cast<float>(fb[r.off + c]), val);
+      }
+      acc = fmaf(wgt, val, acc);
+    }
+    out[static_cast<size_t>(anchor) * d.C + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+template <typename T, int LPG, int U, bool TMA, int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256) ? (1024 / MAXT) : 1)
+    dfa_bwd_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                   const int *__restrict__ start, const float *__restrict__ loc,
+                   const float *__restrict__ weights, const float *__restrict__ grad_out,
+                   float *__restrict__ grad_feat, float *__restrict__ grad_loc,
+                   float *__restrict__ grad_w, Dims d, int overwrite) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  constexpr int TPW = 32 / (4 * LPG);
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, TPW * U, true);
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  TapB *s_rec = reinterpret_cast<TapB *>(smem + lay.rec);
+  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  int *s_list = reinterpret_cast<int *>(smem + lay.list);
+  float2 *s_gl = reinterpret_cast<float2 *>(smem + lay.gl);  // [G][P*K] per-warp rows
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int anchor = blockIdx.x, b = anchor / d.A;
+  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
+  float *gw_a = grad_w + static_cast<size_t>(anchor) * wcount;
+  float *gl_a = grad_loc + static_cast<size_t>(anchor) * PK * 2;
+
+  const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
+                                        weights + static_cast<size_t>(anchor) * wcount, s_w,
+                                        s_loc, s_list, bars, s_nvalid, PK, wcount);
+  const int ntaps = nv * d.L;
+  const int ntaps_pad = (ntaps + TPW * U - 1) / (TPW * U) * (TPW * U);
+
+  if (overwrite) {  // masked samples get explicit zeros: the caller needs no memset
+    for (int i = tid; i < wcount; i += blockDim.x) gw_a[i] = 0.f;
+    for (int i = tid; i < 2 * PK; i += blockDim.x) gl_a[i] = 0.f;
+  }
+  for (int i = tid; i < PK * d.G; i += blockDim.x) s_gl[i] = make_float2(0.f, 0.f);
+  for (int t = tid; t < ntaps_pad; t += blockDim.x) {
+    TapB r;
+    r.off[0] = r.off[1] = r.off[2] = r.off[3] = -1;
+    r.lh = r.lw = r.Wf = r.Hf = 0.f;
+    int widx = 0;
+    if (t < ntaps) {
+      const int l = t / nv, i = t - l * nv, s = s_list[i], k = s % d.K, kl = k * d.L + l;
+      const int H = __ldg(shape + 2 * kl), W = __ldg(shape + 2 * kl + 1);
+      TapGeom gm;
+      tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], H, W, __ldg(start + kl), gm);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r.off[q] = gm.row[q] >= 0 ? gm.row[q] * d.C : -1;
+      r.lh = gm.lh, r.lw = gm.lw, r.Wf = static_cast<float>(W), r.Hf = static_cast<float>(H);
+      widx = (s * d.L + l) * d.G;
+    }
+    s_rec[t] = r;
+    s_widx[t] = widx;
+  }
+  __syncthreads();
+  if (TMA) mbar_wait(&bars[1], 0);
+
+  const int j = lane % LPG, q = (lane / LPG) & 3, sub = lane / (4 * LPG);
+  const int cpg = d.C / d.G;
+  const int choff = g * cpg + j * VEC;
+  const size_t fbase = static_cast<size_t>(b) * d.num_feat * d.C + choff;
+  const T *fb = feat + fbase;
+  float *gfb = grad_feat + fbase;
+  float go[VEC];
+  {
+    const float4 *p = reinterpret_cast<const float4 *>(grad_out + static_cast<size_t>(anchor) * d.C + choff);
+#pragma unroll
+    for (int c = 0; c < VEC / 4; ++c) {
+      const float4 t = __ldg(p + c);
+      go[4 * c] = t.x, go[4 * c + 1] = t.y, go[4 * c + 2] = t.z, go[4 * c + 3] = t.w;
+    }
+  }
+  const bool qh = (q & 2) != 0, qw = (q & 1) != 0;  // corner uses h_high / w_high
+
+  for (int t0 = 0; t0 < ntaps_pad; t0 += TPW * U) {
+    float dsum[U], bwq[U], cxq[U], cyq[U], wgt[U];
+    int widx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * TPW + sub;
+      const int off = s_rec[t].off[q];
+      const float4 fr = *reinterpret_cast<const float4 *>(&s_rec[t].lh);  // lh, lw, W, H
+      widx[u] = s_widx[t] + g;
+      wgt[u] = s_w[widx[u]];
+      const float ah = qh ? fr.x : 1.f - fr.x;  // lh or hh
+      const float aw = qw ? fr.y : 1.f - fr.y;  // lw or hw
+      bwq[u] = ah * aw;
+      cxq[u] = (qw ? ah : -ah) * fr.z;  // d val / d x, already times W
+      cyq[u] = (qh ? aw : -aw) * fr.w;  // d val / d y, already times H
+      float v[VEC];
+      float dd = 0.f;
+      if (off >= 0) {
+        FeatVec<T>::load(fb + off, v);
+        const float coef = bwq[u] * wgt[u];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) dd = fmaf(go[c], v[c], dd);
+#pragma unroll
+        for (int c = 0; c < VEC; c += 4)
+          red_add_v4(gfb + off + c, coef * go[c], coef * go[c + 1], coef * go[c + 2],
+                     coef * go[c + 3]);
+      }
+      dsum[u] = dd;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float dd = dsum[u];
+#pragma unroll
+      for (int m = 1; m < LPG; m <<= 1) dd += __shfl_xor_sync(0xffffffffu, dd, m);
+      float pa = bwq[u] * dd, px = cxq[u] * dd, py = cyq[u] * dd;
+#pragma unroll
+      for (int m = LPG; m < 4 * LPG; m <<= 1) {
+        pa += __shfl_xor_sync(0xffffffffu, pa, m);
+        px += __shfl_xor_sync(0xffffffffu, px, m);
+        py += __shfl_xor_sync(0xffffffffu, py, m);
+      }
+      const int t = t0 + u * TPW + sub;
+      if (j == 0 && q == 0 && t < ntaps) {
+        const int wi = widx[u];
+        if (overwrite) gw_a[wi] = pa; else gw_a[wi] += pa;
+        const int i = t % nv;  // level-major tap order: sample index inside the valid list
+        float2 *cell = &s_gl[g * PK + i];
+        if (TPW == 1) {  // one lane per warp owns the row: plain, ordered accumulation
+          float2 c = *cell;
+          c.x = fmaf(px, wgt[u], c.x), c.y = fmaf(py, wgt[u], c.y);
+          *cell = c;
+        } else {
+          atomicAdd(&cell->x, px * wgt[u]);
+          atomicAdd(&cell->y, py * wgt[u]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nv; i += blockDim.x) {
+    float gx = 0.f, gy = 0.f;
+    for (int w = 0; w < d.G; ++w) gx += s_gl[w * PK + i].x, gy += s_gl[w * PK + i].y;
+    const int s = s_list[i];
+    if (overwrite) {
+      gl_a[2 * s] = gx, gl_a[2 * s + 1] = gy;
+    } else {
+      gl_a[2 * s] += gx, gl_a[2 * s + 1] += gy;
+    }
+  }
+}
+
+// Shape-generic backward: thread per channel, one tap at a time, block-level reductions.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    dfa_bwd_generic_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                           const int *__restrict__ start, const float *__restrict__ loc,
+                           const float *__restrict__ weights, const float *__restrict__ grad_out,
+                           float *__restrict__ grad_feat, float *__restrict__ grad_loc,
+                           float *__restrict__ grad_w, Dims d, int overwrite) {
+  const int anchor = blockIdx.x, b = anchor / d.A, tid = threadIdx.x;
+  const int PK = d.P * d.K, cpg = d.C / d.G;
+  const float *loc_a = loc + static_cast<size_t>(anchor) * PK * 2;
+  const float *w_a = weights + static_cast<size_t>(anchor) * PK * d.L * d.G;
+  float *gw_a = grad_w + static_cast<size_t>(anchor) * PK * d.L * d.G;
+  float *gl_a = grad_loc + static_cast<size_t>(anchor) * PK * 2;
+  const T *fb = feat + static_cast<size_t>(b) * d.num_feat * d.C;
+  float *gfb = grad_feat + static_cast<size_t>(b) * d.num_feat * d.C;
+  const float *go = grad_out + static_cast<size_t>(anchor) * d.C;
+  __shared__ float s_red[3][256];
+  for (int s = 0; s < PK; ++s) {
+    const float x = __ldg(loc_a + 2 * s), y = __ldg(loc_a + 2 * s + 1);
+    const bool ok = sample_valid(x, y);  // uniform across the block
+    float glx = 0.f, gly = 0.f;
+    for (int l = 0; l < d.L; ++l) {
+      const int k = s % d.K, kl = k * d.L + l;
+      float *gw_t = gw_a + (s * d.L + l) * d.G;
+      if (!ok) {
+        if (overwrite)
+          for (int w = tid; w < d.G; w += blockDim.x) gw_t[w] = 0.f;
+        continue;
+      }
+      const int H = __ldg(shape + 2 * kl), W = __ldg(shape + 2 * kl + 1);
+      TapGeom gm;
+      tap_geometry(x, y, H, W, __ldg(start + kl), gm);
+      const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
+      const float cx[4] = {-gm.hh, gm.hh, -gm.lh, gm.lh}, cy[4] = {-gm.hw, -gm.lw, gm.hw, gm.lw};
+      for (int w = 0; w < d.G; ++w) {  // one group at a time keeps the reduction simple
+        float pa = 0.f, px = 0.f, py = 0.f;
+        const float wgt = __ldg(w_a + (s * d.L + l) * d.G + w);
+        for (int c = w * cpg + tid; c < (w + 1) * cpg; c += blockDim.x) {
+          const float gr = __ldg(go + c);
+          for (int q = 0; q < 4; ++q) {
+            if (gm.row[q] < 0) continue;
+            const size_t fi = static_cast<size_t>(gm.row[q]) * d.C + c;
+            const float v = static_cast<float>(fb[fi]);
+            pa = fmaf(bw[q] * gr, v, pa);
+            px = fmaf(cx[q] * gr, v, px);
+            py = fmaf(cy[q] * gr, v, py);
+            atomicAdd(gfb + fi, bw[q] * wgt * gr);
+          }
+        }
+        s_red[0][tid] = pa, s_red[1][tid] = px * wgt * W, s_red[2][tid] = py * wgt * H;
+        __syncthreads();
+        for (int m = blockDim.x / 2; m > 0; m >>= 1) {
+          if (tid < m)
+            for (int r = 0; r < 3; ++r) s_red[r][tid] += s_red[r][tid + m];
+          __syncthreads();
+        }
+        if (tid == 0) {
+          if (overwrite) gw_t[w] = s_red[0][0]; else gw_t[w] += s_red[0][0];
+        }
+        glx += s_red[1][0], gly += s_red[2][0];
+        __syncthreads();
+      }
+    }
+    if (tid == 0) {
+      if (overwrite) {
+        gl_a[2 * s] = glx, gl_a[2 * s + 1] = gly;
+      } else if (ok) {
+        gl_a[2 * s] += glx, gl_a[2 * s + 1] += gly;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// side channel for the bit-exact parity tests: the geometry above, nothing else
+// ------------------------------------------------------------------------------------------
+__global__ void dfa_debug_indices_kernel(const int *__restrict__ shape, const int *__restrict__ start,
+                                         const float *__restrict__ loc, uint8_t *__restrict__ valid,
+                                         int *__restrict__ rows, Dims d) {
+  const long long n = static_cast<long long>(d.bs) * d.A * d.P * d.K;
+  for (long long s = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; s < n;
+       s += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(s % d.K);
+    const float x = loc[2 * s], y = loc[2 * s + 1];
+    const bool ok = sample_valid(x, y);
+    valid[s] = ok ? 1 : 0;
+    for (int l = 0; l < d.L; ++l) {
+      const int kl = k * d.L + l;
+      TapGeom gm;
+      tap_geometry(x, y, shape[2 * kl], shape[2 * kl + 1], start[kl], gm);
+      for (int q = 0; q < 4; ++q) rows[(s * d.L + l) * 4 + q] = ok ? gm.row[q] : -1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// feature-map flattening: NCHW levels → [bs, K*sum(HW), C] channel-last, one pass
+// ------------------------------------------------------------------------------------------
+// A 32(pixels) x 32(channels) tile goes through shared memory so both the NCHW read (pixels
+// contiguous) and the channel-last write (channels contiguous) are coalesced.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+    dfa_flatten_level_kernel(const float *__restrict__ src, TO *__restrict__ dst, int HW, int C,
+                             int K, long long dst_rows_per_batch, int rows_per_cam, int level_row0) {
+  __shared__ float tile[32][33];
+  const int bk = blockIdx.z;  // b * K + k
+  const int b = bk / K, k = bk - b * K;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float *s = src + static_cast<size_t>(bk) * C * HW;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, p = p0 + tx;
+    tile[ty + 8 * i][tx] = (c < C && p < HW) ? __ldg(s + static_cast<size_t>(c) * HW + p) : 0.f;
+  }
+  __syncthreads();
+  TO *o = dst + (static_cast<size_t>(b) * dst_rows_per_batch +
+                 static_cast<size_t>(k) * rows_per_cam + level_row0) * C;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = p0 + ty + 8 * i, c = c0 + tx;
+    if (p < HW && c < C) o[static_cast<size_t>(p) * C + c] = static_cast<TO>(tile[tx][ty + 8 * i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// key points + camera projection
+// ------------------------------------------------------------------------------------------
+// One thread per (b, a, p): builds the 3-D key point, then projects it into the K cameras.
+// Follows models/detection3d/blocks.py:181-207 and models/blocks.py:198-213; the 4-term dot
+// products are evaluated left to right with fused multiply-adds.
+__global__ void __launch_bounds__(256)
+    dfa_keypoints_project_kernel(const float *__restrict__ anchor, const float *__restrict__ fix_scale,
+                                 int num_fix, const float *__restrict__ logits,
+                                 const float *__restrict__ proj, const float *__restrict__ wh,
+                                 float *__restrict__ kp_out, float *__restrict__ loc_out, int bs,
+                                 int A, int P, int K) {
+  const long long n = static_cast<long long>(bs) * A * P;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int p = static_cast<int>(i % P);
+  const long long ba = i / P;
+  const int b = static_cast<int>(ba / A);
+  const float *an = anchor + ba * 11;
+  const float sx = expf(an[3]), sy = expf(an[4]), sz = expf(an[5]);  // W, L, H
+  float ox, oy, oz;
+  if (p < num_fix) {
+    ox = fix_scale[3 * p], oy = fix_scale[3 * p + 1], oz = fix_scale[3 * p + 2];
+  } else {
+    const float *lg = logits + ba * (P - num_fix) * 3 + (p - num_fix) * 3;
+    ox = 1.f / (1.f + expf(-lg[0])) - 0.5f;
+    oy = 1.f / (1.f + expf(-lg[1])) - 0.5f;
+    oz = 1.f / (1.f + expf(-lg[2])) - 0.5f;
+  }
+  ox *= sx, oy *= sy, oz *= sz;
+  const float sn = an[6], cs = an[7];
+  const float x = fmaf(cs, ox, -sn * oy) + an[0];
+  const float y = fmaf(sn, ox, cs * oy) + an[1];
+  const float z = oz + an[2];
+  if (kp_out) kp_out[3 * i] = x, kp_out[3 * i + 1] = y, kp_out[3 * i + 2] = z;
+  for (int k = 0; k < K; ++k) {
+    const float *m = proj + (static_cast<size_t>(b) * K + k) * 16;
+    const float u = fmaf(m[2], z, fmaf(m[1], y, m[0] * x)) + m[3];
+    const float v = fmaf(m[6], z, fmaf(m[5], y, m[4] * x)) + m[7];
+    const float dpt = fmaf(m[10], z, fmaf(m[9], y, m[8] * x)) + m[11];
+    const float den = fmaxf(dpt, 1e-5f);
+    float px = u / den, py = v / den;
+    if (wh) px /= wh[(b * K + k) * 2], py /= wh[(b * K + k) * 2 + 1];
+    float *o = loc_out + (static_cast<size_t>(i) * K + k) * 2;
+    o[0] = px, o[1] = py;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+inline bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+int check_dims(const dfa_dims *dd, Dims &d) {
+  if (!dd) return DFA_ERR_NULL_POINTER;
+  d = Dims{dd->batch_size, dd->num_cams, dd->num_feat, dd->num_embeds,
+           dd->num_scale,  dd->num_anchors, dd->num_pts, dd->num_groups};
+  if (d.bs <= 0 || d.K <= 0 || d.num_feat <= 0 || d.C <= 0 || d.L <= 0 || d.A <= 0 || d.P <= 0 ||
+      d.G <= 0)
+    return DFA_ERR_BAD_DIMS;
+  if (d.C % d.G != 0) return DFA_ERR_BAD_DIMS;
+  // 32-bit element offsets inside one batch item; 31-bit anchor index
+  if (static_cast<long long>(d.num_feat) * d.C >= (1ll << 31)) return DFA_ERR_BAD_DIMS;
+  if (static_cast<long long>(d.bs) * d.A >= (1ll << 31)) return DFA_ERR_BAD_DIMS;
+  if (static_cast<long long>(d.P) * d.K * d.L * d.G >= (1ll << 24)) return DFA_ERR_BAD_DIMS;
+  return 0;
+}
+
+template <typename K>
+int set_smem(K kernel, uint32_t bytes) {
+  if (bytes > 227u * 1024u) return DFA_ERR_UNSUPPORTED;
+  if (bytes > 48u * 1024u) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(bytes));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  return 0;
+}
+
+constexpr int FWD_U = 4;
+constexpr int BWD_U = 2;
+
+template <typename T, int LPG, bool TMA, int MAXT>
+int launch_fwd_t(const void *feat, const int *shape, const int *start, const float *loc,
+                 const float *w, float *out, const Dims &d, cudaStream_t st) {
+  auto kern = dfa_fwd_kernel<T, LPG, FWD_U, TMA, MAXT>;
+  constexpr int TPW = 32 / (4 * LPG);
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, TPW * FWD_U, false);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  kern<<<d.bs * d.A, 32 * d.G, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
+                                               out, d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T, int LPG, bool TMA, int MAXT>
+int launch_bwd_t(const void *feat, const int *shape, const int *start, const float *loc,
+                 const float *w, const float *go, float *gf, float *gl, float *gw, const Dims &d,
+                 int overwrite, cudaStream_t st) {
+  auto kern = dfa_bwd_kernel<T, LPG, BWD_U, TMA, MAXT>;
+  constexpr int TPW = 32 / (4 * LPG);
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, TPW * BWD_U, true);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  kern<<<d.bs * d.A, 32 * d.G, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
+                                               go, gf, gl, gw, d, overwrite);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Fast path applies when a group's channels are a power-of-two number (1..8) of 16-byte vectors
+// and the block (one warp per group) fits; everything else takes the generic kernels.
+template <typename T>
+int fast_lpg(const Dims &d, const void *feat) {
+  const int bytes = (d.C / d.G) * static_cast<int>(sizeof(T));
+  if (bytes % 16 != 0 || !aligned(feat, 16) || d.G > 32) return 0;
+  if ((d.C * static_cast<int>(sizeof(T))) % 16 != 0) return 0;
+  const int lpg = bytes / 16;
+  return (lpg == 1 || lpg == 2 || lpg == 4 || lpg == 8) ? lpg : 0;
+}
+
+inline bool tma_ok(const Dims &d, const float *loc, const float *w) {
+  const long long wbytes = 4ll * d.P * d.K * d.L * d.G, lbytes = 8ll * d.P * d.K;
+  return wbytes % 16 == 0 && lbytes % 16 == 0 && aligned(loc, 16) && aligned(w, 16);
+}
+
+#define DFA_DISPATCH_LPG(CALL)                    \
+  switch (lpg) {                                  \
+    case 8: return CALL(8);                       \
+    case 4: return CALL(4);                       \
+    case 2: return CALL(2);                       \
+    default: return CALL(1);                      \
+  }
+
+template <typename T>
+int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
+                  const float *w, float *out, const Dims &d, cudaStream_t st) {
+  const int lpg = fast_lpg<T>(d, feat);
+  if (lpg && aligned(out, 16)) {
+    const bool tma = tma_ok(d, loc, w);
+    const bool small = 32 * d.G <= 256;
+#define CALL_FWD(N)                                                                            \
+  (tma ? (small ? launch_fwd_t<T, N, true, 256>(feat, shape, start, loc, w, out, d, st)        \
+                : launch_fwd_t<T, N, true, 1024>(feat, shape, start, loc, w, out, d, st))      \
+       : (small ? launch_fwd_t<T, N, false, 256>(feat, shape, start, loc, w, out, d, st)       \
+                : launch_fwd_t<T, N, false, 1024>(feat, shape, start, loc, w, out, d, st)))
+    DFA_DISPATCH_LPG(CALL_FWD)
+#undef CALL_FWD
+  }
+  auto kern = dfa_fwd_generic_kernel<T>;
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, 1, false);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  const int threads = d.C >= 256 ? 256 : ((d.C + 31) / 32) * 32;
+  kern<<<d.bs * d.A, threads, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
+                                              out, d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T>
+int backward_typed(const void *feat, const int *shape, const int *start, const float *loc,
+                   const float *w, const float *go, float *gf, float *gl, float *gw, const Dims &d,
+                   int overwrite, cudaStream_t st) {
+  const int lpg = fast_lpg<T>(d, feat);
+  if (lpg && aligned(go, 16) && aligned(gf, 16) && (d.C * 4) % 16 == 0) {
+    const bool tma = tma_ok(d, loc, w);
+    const bool small = 32 * d.G <= 256;
+#define CALL_BWD(N)                                                                                  \
+  (tma ? (small ? launch_bwd_t<T, N, true, 256>(feat, shape, start, loc, w, go, gf, gl, gw, d,      \
+                                               overwrite, st)                                      \
+                : launch_bwd_t<T, N, true, 1024>(feat, shape, start, loc, w, go, gf, gl, gw, d,     \
+                                                overwrite, st))                                    \
+       : (small ? launch_bwd_t<T, N, false, 256>(feat, shape, start, loc, w, go, gf, gl, gw, d,     \
+                                                overwrite, st)                                     \
+                : launch_bwd_t<T, N, false, 1024>(feat, shape, start, loc, w, go, gf, gl, gw, d,    \
+                                                 overwrite, st)))
+    DFA_DISPATCH_LPG(CALL_BWD)
+#undef CALL_BWD
+  }
+  dfa_bwd_generic_kernel<T><<<d.bs * d.A, 256, 0, st>>>(static_cast<const T *>(feat), shape, start,
+                                                       loc, w, go, gf, gl, gw, d, overwrite);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int dfa_version(void) { return DFA_B200_VERSION; }
+
+const char *dfa_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case DFA_ERR_NULL_POINTER: return "dfa: null pointer argument";
+    case DFA_ERR_BAD_DIMS: return "dfa: bad dimensions (non-positive, C % G != 0, or index overflow)";
+    case DFA_ERR_BAD_DTYPE: return "dfa: unsupported feature dtype";
+    case DFA_ERR_MISALIGNED: return "dfa: pointer not aligned for its element type";
+    case DFA_ERR_UNSUPPORTED: return "dfa: configuration not supported (shared memory budget)";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "dfa: unknown error";
+  }
+}
+
+int dfa_forward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_shape,
+                const int32_t *scale_start_index, const float *sampling_location,
+                const float *weights, float *output, const dfa_dims *dims, void *stream) {
+  if (!mc_ms_feat || !spatial_shape || !scale_start_index || !sampling_location || !weights || !output)
+    return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  if (!aligned(sampling_location, 4) || !aligned(weights, 4) || !aligned(output, 4) ||
+      !aligned(spatial_shape, 4) || !aligned(scale_start_index, 4))
+    return DFA_ERR_MISALIGNED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (feat_dtype == DFA_F32) {
+    if (!aligned(mc_ms_feat, 4)) return DFA_ERR_MISALIGNED;
+    return forward_typed<float>(mc_ms_feat, spatial_shape, scale_start_index, sampling_location,
+                                weights, output, d, st);
+  }
+  if (feat_dtype == DFA_BF16) {
+    if (!aligned(mc_ms_feat, 2)) return DFA_ERR_MISALIGNED;
+    return forward_typed<__nv_bfloat16>(mc_ms_feat, spatial_shape, scale_start_index,
+                                        sampling_location, weights, output, d, st);
+  }
+  return DFA_ERR_BAD_DTYPE;
+}
+
+int dfa_backward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_shape,
+                 const int32_t *scale_start_index, const float *sampling_location,
+                 const float *weights, const float *grad_output, float *grad_mc_ms_feat,
+                 float *grad_sampling_location, float *grad_weights, const dfa_dims *dims,
+                 int flags, void *stream) {
+  if (!mc_ms_feat || !spatial_shape || !scale_start_index || !sampling_location || !weights ||
+      !grad_output || !grad_mc_ms_feat || !grad_sampling_location || !grad_weights)
+    return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  if (!aligned(sampling_location, 4) || !aligned(weights, 4) || !aligned(grad_output, 4) ||
+      !aligned(grad_mc_ms_feat, 4) || !aligned(grad_sampling_location, 4) || !aligned(grad_weights, 4))
+    return DFA_ERR_MISALIGNED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (flags & DFA_BWD_ZERO_GRAD_FEAT) {
+    cudaError_t e = cudaMemsetAsync(grad_mc_ms_feat, 0,
+                                    sizeof(float) * static_cast<size_t>(d.bs) * d.num_feat * d.C, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  const int overwrite = (flags & DFA_BWD_OVERWRITE_SMALL) ? 1 : 0;
+  if (feat_dtype == DFA_F32)
+    return backward_typed<float>(mc_ms_feat, spatial_shape, scale_start_index, sampling_location,
+                                 weights, grad_output, grad_mc_ms_feat, grad_sampling_location,
+                                 grad_weights, d, overwrite, st);
+  if (feat_dtype == DFA_BF16)
+    return backward_typed<__nv_bfloat16>(mc_ms_feat, spatial_shape, scale_start_index,
+                                         sampling_location, weights, grad_output, grad_mc_ms_feat,
+                                         grad_sampling_location, grad_weights, d, overwrite, st);
+  return DFA_ERR_BAD_DTYPE;
+}
+
+int dfa_debug_indices(const int32_t *spatial_shape, const int32_t *scale_start_index,
+                      const float *sampling_location, uint8_t *valid, int32_t *corner_rows,
+                      const dfa_dims *dims, void *stream) {
+  if (!spatial_shape || !scale_start_index || !sampling_location || !valid || !corner_rows)
+    return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  const long long n = static_cast<long long>(d.bs) * d.A * d.P * d.K;
+  const int blocks = static_cast<int>((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  dfa_debug_indices_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      spatial_shape, scale_start_index, sampling_location, valid, corner_rows, d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int dfa_flatten_maps(const float *const *level_ptrs, const int32_t *level_hw, int num_levels,
+                     int bs, int num_cams, int channels, void *col_feats, int out_dtype,
+                     void *stream) {
+  if (!level_ptrs || !level_hw || !col_feats) return DFA_ERR_NULL_POINTER;
+  if (num_levels <= 0 || bs <= 0 || num_cams <= 0 || channels <= 0) return DFA_ERR_BAD_DIMS;
+  if (out_dtype != DFA_F32 && out_dtype != DFA_BF16) return DFA_ERR_BAD_DTYPE;
+  long long rows_per_cam = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    if (!level_ptrs[l]) return DFA_ERR_NULL_POINTER;
+    if (level_hw[2 * l] <= 0 || level_hw[2 * l + 1] <= 0) return DFA_ERR_BAD_DIMS;
+    rows_per_cam += static_cast<long long>(level_hw[2 * l]) * level_hw[2 * l + 1];
+  }
+  if (rows_per_cam * num_cams >= (1ll << 31) || static_cast<long long>(bs) * num_cams > 65535)
+    return DFA_ERR_BAD_DIMS;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int row0 = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int HW = level_hw[2 * l] * level_hw[2 * l + 1];
+    dim3 grid((HW + 31) / 32, (channels + 31) / 32, bs * num_cams);
+    if (grid.y > 65535) return DFA_ERR_BAD_DIMS;
+    if (out_dtype == DFA_F32)
+      dfa_flatten_level_kernel<float><<<grid, 256, 0, st>>>(
+          level_ptrs[l], static_cast<float *>(col_feats), HW, channels, num_cams,
+          rows_per_cam * num_cams, static_cast<int>(rows_per_cam), row0);
+    else
+      dfa_flatten_level_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+          level_ptrs[l], static_cast<__nv_bfloat16 *>(col_feats), HW, channels, num_cams,
+          rows_per_cam * num_cams, static_cast<int>(rows_per_cam), row0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    row0 += HW;
+  }
+  return 0;
+}
+
+int dfa_keypoints_project(const float *anchor, const float *fix_scale, int num_fix,
+                          const float *learnable_logits, const float *projection_mat,
+                          const float *image_wh, float *key_points, float *sampling_location,
+                          int bs, int num_anchors, int num_pts, int num_cams, void *stream) {
+  if (!anchor || !fix_scale || !projection_mat || !sampling_location) return DFA_ERR_NULL_POINTER;
+  if (bs <= 0 || num_anchors <= 0 || num_pts <= 0 || num_cams <= 0 || num_fix < 0 || num_fix > num_pts)
+    return DFA_ERR_BAD_DIMS;
+  if (num_fix < num_pts && !learnable_logits) return DFA_ERR_NULL_POINTER;
+  const long long n = static_cast<long long>(bs) * num_anchors * num_pts;
+  if (n >= (1ll << 31)) return DFA_ERR_BAD_DIMS;
+  dfa_keypoints_project_kernel<<<static_cast<int>((n + 255) / 256), 256, 0,
+                                 static_cast<cudaStream_t>(stream)>>>(
+      anchor, fix_scale, num_fix, learnable_logits, projection_mat, image_wh, key_points,
+      sampling_location, bs, num_anchors, num_pts, num_cams);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int64_t dfa_forward_host_workspace_bytes(int feat_dtype, const dfa_dims *dims) {
+  Dims d;
+  if (check_dims(dims, d)) return -1;
+  const int64_t esz = feat_dtype == DFA_BF16 ? 2 : 4;
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  return up(esz * d.bs * d.num_feat * d.C) + up(8ll * d.K * d.L) + up(4ll * d.K * d.L) +
+         up(8ll * d.bs * d.A * d.P * d.K) + up(4ll * d.bs * d.A * d.P * d.K * d.L * d.G) +
+         up(4ll * d.bs * d.A * d.C);
+}
+
+int dfa_forward_host(const void *h_feat, int feat_dtype, const int32_t *h_shape,
+                     const int32_t *h_start, const float *h_loc, const float *h_w, float *h_out,
+                     const dfa_dims *dims, void *workspace, int64_t workspace_bytes, void *stream) {
+  if (!h_feat || !h_shape || !h_start || !h_loc || !h_w || !h_out || !workspace)
+    return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  if (feat_dtype != DFA_F32 && feat_dtype != DFA_BF16) return DFA_ERR_BAD_DTYPE;
+  if (workspace_bytes < dfa_forward_host_workspace_bytes(feat_dtype, dims)) return DFA_ERR_BAD_DIMS;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t esz = feat_dtype == DFA_BF16 ? 2 : 4;
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  char *p = static_cast<char *>(workspace);
+  const int64_t nb_feat = esz * d.bs * d.num_feat * d.C, nb_shape = 8ll * d.K * d.L,
+                nb_start = 4ll * d.K * d.L, nb_loc = 8ll * d.bs * d.A * d.P * d.K,
+                nb_w = 4ll * d.bs * d.A * d.P * d.K * d.L * d.G, nb_out = 4ll * d.bs * d.A * d.C;
+  void *d_feat = p; p += up(nb_feat);
+  int32_t *d_shape = reinterpret_cast<int32_t *>(p); p += up(nb_shape);
+  int32_t *d_start = reinterpret_cast<int32_t *>(p); p += up(nb_start);
+  float *d_loc = reinterpret_cast<float *>(p); p += up(nb_loc);
+  float *d_w = reinterpret_cast<float *>(p); p += up(nb_w);
+  float *d_out = reinterpret_cast<float *>(p);
+  cudaError_t e;
+  // small operands first so the kernel's staging data is resident before the big copy ends
+  if ((e = cudaMemcpyAsync(d_shape, h_shape, nb_shape, cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemcpyAsync(d_start, h_start, nb_start, cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemcpyAsync(d_loc, h_loc, nb_loc, cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemcpyAsync(d_w, h_w, nb_w, cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemcpyAsync(d_feat, h_feat, nb_feat, cudaMemcpyHostToDevice, st))) return e;
+  if (int rc = dfa_forward(d_feat, feat_dtype, d_shape, d_start, d_loc, d_w, d_out, dims, stream))
+    return rc;
+  if ((e = cudaMemcpyAsync(h_out, d_out, nb_out, cudaMemcpyDeviceToHost, st))) return e;
+  return static_cast<int>(cudaStreamSynchronize(st));
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+"""Drop-in for the reference's `projects/mmdet3d_plugin/ops` package: same three public names,
+same argument order and meaning (/root/reference/projects/mmdet3d_plugin/ops/__init__.py)."""
+import torch
+
+from .. import cabi
+from .deformable_aggregation import DeformableAggregationFunction
+
+__all__ = ["DeformableAggregationFunction", "deformable_aggregation_function",
+           "feature_maps_format"]
+
+
+def deformable_aggregation_function(feature_maps, spatial_shape, scale_start_index,
+                                    sampling_location, weights):
+    """ops/__init__.py:6-19 — (mc_ms_feat [bs,num_feat,C], spatial_shape [K,L,2],
+    scale_start_index [K,L], sampling_location [bs,A,P,K,2], weights [bs,A,P,K,L,G])
+    → [bs, A, C] float32, differentiable wrt features, locations and weights."""
+    return DeformableAggregationFunction.apply(feature_maps, spatial_shape, scale_start_index,
+                                               sampling_location, weights)
+
+
+def _tables(sizes, num_cams, device):
+    shape = torch.tensor([list(sizes)] * num_cams, dtype=torch.int64, device=device)
+    counts = (shape[..., 0] * shape[..., 1]).flatten()
+    start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]]).reshape(num_cams, -1)
+    return shape, start
+
+
+def feature_maps_format(feature_maps, inverse=False, dtype=None):
+    """ops/__init__.py:22-92.  Forward direction: a list over levels of [bs, K, C, H_l, W_l] maps
+    becomes [col_feats [bs, K*sum(H_l*W_l), C], spatial_shape [K,L,2] int64, scale_start_index
+    [K,L] int64] with col_feats[b, start[k,l] + y*W_l + x, c] == maps[l][b,k,c,y,x] — done here by
+    ONE transposing kernel per level writing straight into the final buffer (the reference does
+    reshape + cat + permute + flatten).  `dtype=torch.bfloat16` emits a bf16 table (extension).
+    A list of lists (camera groups with different resolutions) is formatted group by group and
+    concatenated, as the reference does (:56-61).  inverse=True returns the nested list
+    `[[level maps of camera group 0], ...]` of [bs, n_cam, C, H, W] views (:23-54)."""
+    if inverse:
+        col, shape, start = feature_maps
+        K, L = shape.shape[:2]
+        sizes = shape.tolist()
+        starts = start.tolist()
+        bs, _, C = col.shape
+        groups, k = [], 0
+        while k < K:   # consecutive cameras with identical level sizes form one group
+            k1 = k + 1
+            while k1 < K and sizes[k1] == sizes[k]:
+                k1 += 1
+            per_cam = sum(h * w for h, w in sizes[k])
+            block = col[:, starts[k][0]:starts[k][0] + (k1 - k) * per_cam]
+            block = block.reshape(bs, k1 - k, per_cam, C)
+            levels, o = [], 0
+            for h, w in sizes[k]:
+                levels.append(block[:, :, o:o + h * w].reshape(bs, k1 - k, h, w, C)
+                              .permute(0, 1, 4, 2, 3))
+                o += h * w
+            groups.append(levels)
+            k = k1
+        return groups
+
+    if isinstance(feature_maps[0], (list, tuple)):
+        parts = [feature_maps_format(x, dtype=dtype) for x in feature_maps]
+        col = torch.cat([p[0] for p in parts], dim=1)
+        shape = torch.cat([p[1] for p in parts], dim=0)
+        counts = (shape[..., 0] * shape[..., 1]).flatten()
+        start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]]).reshape(shape.shape[0], -1)
+        return [col, shape, start]
+
+    maps = [m.contiguous().float() for m in feature_maps]
+    K = maps[0].shape[1]
+    col = cabi.flatten_maps(maps, out_dtype=dtype or torch.float32)
+    shape, start = _tables([tuple(m.shape[-2:]) for m in maps], K, col.device)
+    return [col, shape, start]

@@ -1,0 +1,75 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol the header
+declares, validates arguments without touching a GPU, and the product package never reaches
+into the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_build_products_exist():
+    from simpb_b200 import build
+    lib, ext = build.build_all()
+    assert os.path.exists(lib) and os.path.exists(ext)
+
+
+def test_library_exports_every_declared_symbol():
+    from simpb_b200 import cabi
+    header = open(os.path.join(ROOT, "include", "dfa_b200.h")).read()
+    declared = set(re.findall(r"\b(dfa_[a-z_]+)\s*\(", header))
+    assert declared == set(cabi.SYMBOLS), declared ^ set(cabi.SYMBOLS)
+    raw = ctypes.CDLL(cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert cabi.lib.dfa_version() == 100
+
+
+def test_argument_validation_needs_no_gpu():
+    from simpb_b200 import cabi
+    d = cabi.Dims(1, 6, 100, 256, 4, 9, 13, 8)
+    rc = cabi.lib.dfa_forward(None, 0, None, None, None, None, None, ctypes.byref(d), None)
+    assert rc == -1 and b"null" in cabi.lib.dfa_error_string(rc)
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    bad = cabi.Dims(1, 6, 100, 250, 4, 9, 13, 8)          # C % G != 0
+    assert cabi.lib.dfa_forward(p, 0, p, p, p, p, p, ctypes.byref(bad), None) == -2
+    zero = cabi.Dims(0, 6, 100, 256, 4, 9, 13, 8)          # empty batch
+    assert cabi.lib.dfa_forward(p, 0, p, p, p, p, p, ctypes.byref(zero), None) == -2
+    big = cabi.Dims(1, 6, 1 << 24, 256, 4, 9, 13, 8)       # 32-bit offset overflow
+    assert cabi.lib.dfa_forward(p, 0, p, p, p, p, p, ctypes.byref(big), None) == -2
+    assert cabi.lib.dfa_forward(p, 7, p, p, p, p, p, ctypes.byref(d), None) == -3
+    assert cabi.lib.dfa_forward(p + 2, 0, p, p, p, p, p, ctypes.byref(d), None) == -4
+    assert cabi.lib.dfa_forward_host_workspace_bytes(0, ctypes.byref(d)) > 4 * 100 * 256
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from simpb_b200 import cabi, deformable_aggregation_function
+    t = torch.zeros(1, 4, 8)
+    with pytest.raises(cabi.DfaError):
+        cabi.forward(t, torch.zeros(1, 1, 2, dtype=torch.int32), torch.zeros(1, 1, dtype=torch.int32),
+                     torch.zeros(1, 1, 1, 1, 2), torch.zeros(1, 1, 1, 1, 1, 2))
+    with pytest.raises(cabi.DfaError):
+        deformable_aggregation_function(t, torch.zeros(1, 1, 2), torch.zeros(1, 1),
+                                        torch.zeros(1, 1, 1, 1, 2), torch.zeros(1, 1, 1, 1, 1, 2))
+
+
+def test_torch_extension_has_reference_entry_points():
+    from simpb_b200.ops import deformable_aggregation_ext as ext
+    assert callable(ext.deformable_aggregation_forward)
+    assert callable(ext.deformable_aggregation_backward)
+    with pytest.raises(RuntimeError):
+        ext.deformable_aggregation_forward(*[torch.zeros(1)] * 5)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "simpb_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "oracle/" not in src and "dfa_oracle" not in src, f

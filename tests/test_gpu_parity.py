@@ -1,0 +1,445 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, the golden fixtures and — when
+the prebuilt object is present — the unmodified reference CUDA op."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import module_ref
+from helpers import (RTOL_BF16, RTOL_F32, assert_close, golden_op_inputs, load_golden, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(d, dtype=torch.float32):
+    """Move an op-input dict to the GPU in the dtypes the C ABI takes."""
+    from simpb_b200 import synthetic  # noqa: F401
+    g = {}
+    g["feat"] = d["mc_ms_feat"].cuda().to(dtype).contiguous()
+    g["shape"] = d["spatial_shape"].int().cuda()
+    g["start"] = d["scale_start_index"].int().cuda()
+    g["loc"] = d["sampling_location"].cuda().contiguous()
+    g["w"] = d["weights"].cuda().contiguous()
+    g["go"] = d["grad_output"].cuda().contiguous()
+    return g
+
+
+def small_case(seed, bs, A, P, K, sizes, C, G, lo=-0.15, hi=1.15):
+    from simpb_b200 import synthetic
+    return synthetic.op_inputs_uniform(bs=bs, A=A, P=P, K=K, levels=sizes, C=C, G=G, seed=seed,
+                                       lo=lo, hi=hi)
+
+
+def check_case(d, dtype=torch.float32, rtol=RTOL_F32, backward=True):
+    from simpb_b200 import cabi
+    g = dev(d, dtype)
+    feat_ref = g["feat"].float().cpu()      # the oracle sees exactly the values the kernel sees
+    out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    ref = oracle.forward(feat_ref, d["spatial_shape"], d["scale_start_index"],
+                         d["sampling_location"], d["weights"])
+    assert_close(out, ref, rtol if dtype == torch.float32 else RTOL_F32, "forward")
+    if not backward:
+        return
+    rgf, rgl, rgw = oracle.backward(feat_ref, d["spatial_shape"], d["scale_start_index"],
+                                    d["sampling_location"], d["weights"], d["grad_output"])
+    # (1) library-managed buffers: small gradients fully written, grad_feat zeroed by the library
+    gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    assert_close(gf, rgf, rtol, "grad_feat")
+    assert_close(gl, rgl, rtol, "grad_loc")
+    assert_close(gw, rgw, rtol, "grad_weights")
+    # (2) reference contract: accumulate into caller-provided buffers (here pre-filled with 1)
+    gf2 = torch.ones_like(gf); gl2 = torch.ones_like(gl); gw2 = torch.ones_like(gw)
+    cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"], gf2, gl2, gw2)
+    assert_close(gf2 - 1, rgf, 4 * rtol, "grad_feat (accumulate)")
+    assert_close(gl2 - 1, rgl, 4 * rtol, "grad_loc (accumulate)")
+    assert_close(gw2 - 1, rgw, 4 * rtol, "grad_weights (accumulate)")
+
+
+# ------------------------------------------------------------------ indices / masks: bit-exact
+def tie_locations(sizes, n=4096, seed=0):
+    """Locations whose pixel coordinate sits within a few ulp of an integer or of the (0,1)
+    borders — where the one-rounding FMA and a two-rounding evaluation can disagree."""
+    rng = np.random.default_rng(seed)
+    vals = []
+    for h, w in sizes:
+        for size in (h, w):
+            k = rng.integers(0, size, n // 8)
+            base = ((k + 0.5) / size).astype(np.float32)
+            for ulps in (-2, -1, 0, 1, 2):
+                v = base.copy()
+                for _ in range(abs(ulps)):
+                    v = np.nextafter(v, np.float32(2.0 if ulps > 0 else -2.0))
+                vals.append(v)
+    vals.append(np.array([0.0, 1.0, np.nextafter(np.float32(0), np.float32(1)),
+                          np.nextafter(np.float32(1), np.float32(0)), -0.0, 1e-30, 0.5],
+                         np.float32))
+    v = np.concatenate(vals)
+    rng.shuffle(v)
+    return v
+
+
+def test_indices_and_masks_bit_exact_r50():
+    from simpb_b200 import cabi, synthetic
+    for maker, seed in ((synthetic.op_inputs_uniform, 0), (synthetic.rig_op_inputs, 1)):
+        d = maker(bs=2, seed=seed, feat=False)
+        valid, rows = cabi.debug_indices(d["spatial_shape"].int().cuda(),
+                                         d["scale_start_index"].int().cuda(),
+                                         d["sampling_location"].cuda())
+        dummy = np.zeros((2, d["num_feat"], 8), np.float32)
+        _, rv, rr = oracle.forward(dummy, d["spatial_shape"], d["scale_start_index"],
+                                   d["sampling_location"], np.zeros(d["weights"].shape[:5] + (8,), np.float32),
+                                   side_channel=True)
+        np.testing.assert_array_equal(valid.cpu().numpy(), rv)
+        np.testing.assert_array_equal(rows.cpu().numpy(), rr)
+
+
+def test_indices_bit_exact_on_rounding_ties():
+    from simpb_b200 import cabi, synthetic
+    shape, start, num_feat = synthetic.level_tables(synthetic.R50_LEVELS, 6)
+    v = tie_locations(synthetic.R50_LEVELS)
+    n = (len(v) // (13 * 6 * 2)) * (13 * 6 * 2)
+    loc = torch.from_numpy(v[:n].copy()).reshape(1, -1, 13, 6, 2)
+    valid, rows = cabi.debug_indices(shape.int().cuda(), start.int().cuda(), loc.cuda())
+    A = loc.shape[1]
+    _, rv, rr = oracle.forward(np.zeros((1, num_feat, 8), np.float32), shape, start, loc,
+                               np.zeros((1, A, 13, 6, 4, 8), np.float32), side_channel=True)
+    np.testing.assert_array_equal(valid.cpu().numpy(), rv)
+    np.testing.assert_array_equal(rows.cpu().numpy(), rr)
+
+
+# ------------------------------------------------------------------ floating parity vs the oracle
+SIZES3 = ((8, 12), (4, 6), (2, 3))
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(bs=2, A=7, P=5, K=3, sizes=SIZES3, C=32, G=4),      # 2 vector lanes per group row
+    dict(bs=1, A=33, P=13, K=6, sizes=SIZES3, C=256, G=8),   # released group geometry (8 lanes)
+    dict(bs=3, A=5, P=4, K=2, sizes=SIZES3, C=64, G=4),      # 4 lanes per group row
+    dict(bs=1, A=9, P=3, K=2, sizes=SIZES3, C=20, G=5),      # 1 lane per group row
+    dict(bs=2, A=4, P=3, K=1, sizes=((5, 7),), C=6, G=3),    # generic kernels (2 channels / group)
+    dict(bs=1, A=6, P=3, K=3, sizes=SIZES3, C=32, G=1),      # weights block not 16-byte sized: no TMA
+    dict(bs=1, A=3, P=32, K=6, sizes=SIZES3, C=256, G=8),    # many key points
+    dict(bs=1, A=2, P=2, K=2, sizes=SIZES3, C=512, G=16),    # 16 warps per anchor
+])
+def test_small_shapes_vs_oracle(cfg):
+    check_case(small_case(11, **cfg))
+
+
+def test_r50_shape_uniform_vs_oracle():
+    from simpb_b200 import synthetic
+    check_case(synthetic.op_inputs_uniform(bs=1, seed=0))
+
+
+def test_r50_shape_rig_vs_oracle():
+    from simpb_b200 import synthetic
+    check_case(synthetic.rig_op_inputs(bs=2, seed=3))
+
+
+def test_training_anchor_count_vs_oracle():
+    from simpb_b200 import synthetic
+    check_case(synthetic.rig_op_inputs(bs=1, A=1220, seed=4))
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(bs=2, A=7, P=5, K=3, sizes=SIZES3, C=32, G=4),
+    dict(bs=1, A=33, P=13, K=6, sizes=SIZES3, C=256, G=8),
+    dict(bs=1, A=5, P=3, K=2, sizes=SIZES3, C=24, G=4),      # 6 bf16 per group: generic kernel
+])
+def test_bf16_features_vs_oracle(cfg):
+    d = small_case(12, **cfg)
+    # against the oracle on the bf16-rounded values: fp32 tolerance (the arithmetic is fp32) …
+    check_case(d, dtype=torch.bfloat16, rtol=RTOL_F32)
+    # … and against the fp32 features: the north-star 1e-2 bound
+    from simpb_b200 import cabi
+    g = dev(d, torch.bfloat16)
+    out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    ref = oracle.forward(d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"],
+                         d["sampling_location"], d["weights"])
+    assert_close(out, ref, RTOL_BF16, "bf16 features vs fp32 oracle")
+
+
+@pytest.mark.parametrize("name", ["op_masked_f64", "op_masked_f32", "op_inner_f64"])
+def test_golden_reference_fixtures(name):
+    """The reference's own grid_sample path (fixtures made by tests/golden/make_golden.py)."""
+    from simpb_b200 import cabi
+    g = load_golden(name)
+    col, shape, start, gcol = golden_op_inputs(g)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().cuda()  # noqa: E731
+    out = cabi.forward(col.cuda(), shape.int().cuda(), start.int().cuda(), t(g["loc"]), t(g["weights"]))
+    assert_close(out, g["out"], RTOL_F32, name)
+    gf, gl, gw = cabi.backward(col.cuda(), shape.int().cuda(), start.int().cuda(), t(g["loc"]),
+                               t(g["weights"]), t(g["grad_out"]))
+    assert_close(gf, gcol.numpy(), RTOL_F32, name + " grad_feat")
+    assert_close(gw, g["grad_weights"], RTOL_F32, name + " grad_weights")
+    assert_close(gl, g["grad_loc"], 5 * RTOL_F32, name + " grad_loc")
+
+
+# ------------------------------------------------------------------ edge cases
+def test_all_samples_masked_gives_zeros():
+    from simpb_b200 import cabi
+    d = small_case(5, bs=1, A=4, P=3, K=2, sizes=SIZES3, C=32, G=4, lo=1.0, hi=1.5)
+    g = dev(d)
+    out = torch.full((1, 4, 32), 7.0, device="cuda")
+    cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=out)
+    assert (out == 0).all()
+    gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    assert (gf == 0).all() and (gl == 0).all() and (gw == 0).all()
+
+
+def test_border_values_are_excluded():
+    """loc exactly 0 or 1 is masked (exclusive test, …_cuda.cu:168-171)."""
+    from simpb_b200 import cabi
+    d = small_case(6, bs=1, A=2, P=2, K=1, sizes=((4, 4),), C=32, G=4, lo=0.2, hi=0.8)
+    loc = d["sampling_location"]
+    loc[0, 0, 0, 0, 0] = 0.0
+    loc[0, 0, 1, 0, 1] = 1.0
+    loc[0, 1, 0, 0, 0] = float(np.nextafter(np.float32(1), np.float32(0)))   # still valid
+    check_case(d)
+    valid, _ = cabi.debug_indices(d["spatial_shape"].int().cuda(), d["scale_start_index"].int().cuda(),
+                                  loc.cuda())
+    assert valid.flatten().tolist() == [0, 0, 1, 1]
+
+
+def test_output_buffer_needs_no_zero_fill():
+    from simpb_b200 import cabi
+    d = small_case(7, bs=2, A=5, P=3, K=2, sizes=SIZES3, C=64, G=8)
+    g = dev(d)
+    a = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    junk = torch.full_like(a, float("nan"))
+    b = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=junk)
+    assert torch.equal(a, b)
+
+
+def test_forward_is_deterministic():
+    from simpb_b200 import cabi, synthetic
+    g = dev(synthetic.op_inputs_uniform(bs=1, A=300, seed=2))
+    a = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    for _ in range(3):
+        assert torch.equal(a, cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"]))
+    # the two small gradients are produced without atomics: bitwise reproducible as well
+    _, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    _, gl2, gw2 = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    assert torch.equal(gl, gl2) and torch.equal(gw, gw2)
+
+
+# ------------------------------------------------------------------ size-independent properties
+def test_full_size_properties_bs8():
+    """Training shape (bs=8, A=1220): linearity in features and weights, batch independence."""
+    from simpb_b200 import cabi, synthetic
+    d = synthetic.rig_op_inputs(bs=8, A=1220, seed=9)
+    g = dev(d)
+    f = lambda feat, w: cabi.forward(feat, g["shape"], g["start"], g["loc"], w)  # noqa: E731
+    base = f(g["feat"], g["w"])
+    assert_close(f(g["feat"] * 2, g["w"]), (2 * base), 1e-6, "linear in features")
+    assert_close(f(g["feat"], g["w"] * 0.5), (0.5 * base), 1e-6, "linear in weights")
+    other = torch.randn_like(g["feat"])
+    assert_close(f(g["feat"] + other, g["w"]), base + f(other, g["w"]), 2e-6, "additive in features")
+    # batch items are independent: item 3 alone reproduces row 3 bit for bit
+    one = cabi.forward(g["feat"][3:4].contiguous(), g["shape"], g["start"],
+                       g["loc"][3:4].contiguous(), g["w"][3:4].contiguous())
+    assert torch.equal(one[0], base[3])
+    # anchors are independent: reversing anchor order reverses the output
+    rev = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"].flip(1).contiguous(),
+                       g["w"].flip(1).contiguous())
+    assert torch.equal(rev.flip(1), base)
+    # adjoint identity <out, go> == <w, grad_w> (out is linear in w)
+    _, _, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    lhs = (base.double() * g["go"].double()).sum()
+    rhs = (g["w"].double() * gw.double()).sum()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+# ------------------------------------------------------------------ python surface
+def test_autograd_function_and_torch_extension():
+    from simpb_b200 import deformable_aggregation_function
+    from simpb_b200.ops import deformable_aggregation_ext as ext
+    d = small_case(13, bs=2, A=6, P=4, K=3, sizes=SIZES3, C=64, G=8)
+    g = dev(d)
+    feat = g["feat"].clone().requires_grad_()
+    loc = g["loc"].clone().requires_grad_()
+    w = g["w"].clone().requires_grad_()
+    # int64 tables straight from feature_maps_format are accepted, as in the reference
+    out = deformable_aggregation_function(feat, d["spatial_shape"].cuda(), d["scale_start_index"].cuda(),
+                                          loc, w)
+    out.backward(g["go"])
+    rgf, rgl, rgw = oracle.backward(d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"],
+                                    d["sampling_location"], d["weights"], d["grad_output"])
+    assert_close(feat.grad, rgf, RTOL_F32, "autograd grad_feat")
+    assert_close(loc.grad, rgl, RTOL_F32, "autograd grad_loc")
+    assert_close(w.grad, rgw, RTOL_F32, "autograd grad_weights")
+    # the pybind module with the reference's two entry points
+    o2 = ext.deformable_aggregation_forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    assert torch.equal(o2, out.detach())
+    gf = torch.zeros_like(g["feat"]); gl = torch.zeros_like(g["loc"]); gw = torch.zeros_like(g["w"])
+    ext.deformable_aggregation_backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
+                                        gf, gl, gw)
+    assert_close(gf, rgf, RTOL_F32, "ext grad_feat")
+    assert torch.equal(gl, loc.grad) and torch.equal(gw, w.grad)
+    with pytest.raises(RuntimeError):
+        ext.deformable_aggregation_forward(g["feat"], g["shape"].long(), g["start"], g["loc"], g["w"])
+
+
+def test_runs_on_a_side_stream():
+    from simpb_b200 import cabi
+    d = small_case(14, bs=1, A=50, P=13, K=6, sizes=SIZES3, C=256, G=8)
+    g = dev(d)
+    ref = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    s.synchronize()
+    assert torch.equal(out, ref)
+
+
+def test_host_buffer_entry_point():
+    from simpb_b200 import cabi
+    d = small_case(15, bs=2, A=9, P=13, K=6, sizes=SIZES3, C=256, G=8)
+    dims = cabi.Dims(2, 6, d["num_feat"], 256, 3, 9, 13, 8)
+    hf = cabi.HostForward(dims)
+    pin = lambda t: t.contiguous().pin_memory()  # noqa: E731
+    h_out = torch.empty(2, 9, 256).pin_memory()
+    hf(pin(d["mc_ms_feat"]), pin(d["spatial_shape"].int()), pin(d["scale_start_index"].int()),
+       pin(d["sampling_location"]), pin(d["weights"]), h_out)
+    ref = oracle.forward(d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"],
+                         d["sampling_location"], d["weights"])
+    assert_close(h_out, ref, RTOL_F32, "dfa_forward_host")
+
+
+# ------------------------------------------------------------------ flatten / key points
+def test_flatten_maps_matches_reference_layout():
+    from simpb_b200 import feature_maps_format
+    g = load_golden("flatten_small")
+    maps = [torch.from_numpy(g["map%d" % l]).cuda() for l in range(g["sizes"].shape[0])]
+    col, shape, start = feature_maps_format(maps)
+    assert shape.dtype == torch.int64 and start.dtype == torch.int64
+    np.testing.assert_array_equal(col.cpu().numpy(), g["col"])        # data movement: bit-exact
+    np.testing.assert_array_equal(shape.cpu().numpy(), g["shape"])
+    np.testing.assert_array_equal(start.cpu().numpy(), g["start"])
+    back = feature_maps_format([col, shape, start], inverse=True)
+    assert len(back) == int(g["inverse_n_groups"]) and len(back[0]) == int(g["inverse_n_levels"])
+    for l, m in enumerate(back[0]):
+        np.testing.assert_array_equal(m.cpu().numpy(), g["inv%d" % l])
+    colh, _, _ = feature_maps_format(maps, dtype=torch.bfloat16)
+    assert torch.equal(colh, col.bfloat16())
+
+
+def test_flatten_maps_r50_shape():
+    from simpb_b200 import feature_maps_format, synthetic
+    gen = torch.Generator().manual_seed(0)
+    maps = [torch.randn(1, 6, 256, h, w, generator=gen) for h, w in synthetic.R50_LEVELS]
+    col, shape, start = feature_maps_format([m.cuda() for m in maps])
+    rcol, rshape, rstart = module_ref.flatten_feature_maps(maps)
+    assert torch.equal(col.cpu(), rcol) and torch.equal(shape.cpu(), rshape)
+    assert torch.equal(start.cpu(), rstart)
+
+
+def test_keypoints_project_vs_oracle():
+    from simpb_b200 import cabi, synthetic
+    d = synthetic.module_inputs_rig(bs=2, A=900, seed=5, feat=False)
+    gen = torch.Generator().manual_seed(6)
+    logits = torch.randn(2, 900, 18, generator=gen)
+    fix = torch.tensor(synthetic.FIX_SCALE)
+    loc, kp = cabi.keypoints_project(d["anchor"].cuda(), fix.cuda(), logits.cuda(),
+                                     d["projection_mat"].cuda(), d["image_wh"].cuda(),
+                                     want_key_points=True)
+    rkp = module_ref.key_points(d["anchor"].double(), fix.double(), logits.double())
+    ruv = module_ref.project_points(rkp, d["projection_mat"].double(), d["image_wh"].double())
+    ruv = ruv.permute(0, 2, 3, 1, 4)
+    assert_close(kp, rkp, 1e-6, "key points")
+    # compare where the projection is well conditioned (in front of the camera, O(1) coords)
+    sel = (ruv.abs() < 3).all(-1)
+    err = (loc.cpu().double() - ruv)[sel].abs().max()
+    assert err < 2e-5, err
+    # validity masks: identical except for points within rounding distance of a border
+    mine = module_ref.op_valid_mask(loc.cpu())
+    ref = module_ref.op_valid_mask(ruv.float())
+    flips = (mine != ref)
+    if flips.any():
+        dist = torch.minimum(ruv.abs(), (ruv - 1).abs()).min(-1).values
+        assert (dist[flips] < 1e-5).all()
+    assert flips.float().mean() < 1e-4
+
+
+# ------------------------------------------------------------------ the unmodified reference op
+def _ref_ext():
+    from oracle import build_ref
+    if not os.path.exists(build_ref.so_path()):
+        pytest.skip("oracle/_ref/ not built (needs /root/reference at build time)")
+    return build_ref.load()
+
+
+def test_against_reference_cuda_op_r50():
+    from simpb_b200 import cabi, synthetic
+    ref_ext = _ref_ext()
+    for d in (synthetic.op_inputs_uniform(bs=1, seed=0), synthetic.rig_op_inputs(bs=2, seed=1)):
+        g = dev(d)
+        out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+        rout = ref_ext.deformable_aggregation_forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+        o64 = oracle.forward(d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"],
+                             d["sampling_location"], d["weights"])
+        assert_close(out, rout, RTOL_F32, "forward vs reference op")
+        assert_close(rout, o64, RTOL_F32, "reference op vs oracle")
+        gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+        rgf = torch.zeros_like(g["feat"]); rgl = torch.zeros_like(g["loc"]); rgw = torch.zeros_like(g["w"])
+        ref_ext.deformable_aggregation_backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"],
+                                                g["go"], rgf, rgl, rgw)
+        assert_close(gf, rgf, RTOL_F32, "grad_feat vs reference op")
+        assert_close(gw, rgw, RTOL_F32, "grad_weights vs reference op")
+        assert_close(gl, rgl, 2 * RTOL_F32, "grad_loc vs reference op")
+
+
+def test_reference_binary_pins_indices_and_masks():
+    """Bit-exact index/mask pin against the reference BINARY.  Every (a,p,k) sample gets a private
+    channel (G == C, one-hot weights and grad_output), so the non-zero pattern of the reference
+    op's grad_mc_ms_feat[b, :, channel] is exactly the set of rows that sample touched.  Uses
+    rounding-tie locations, where a two-rounding evaluation of loc*size-0.5 would differ."""
+    from simpb_b200 import cabi, synthetic
+    ref_ext = _ref_ext()
+    sizes = synthetic.R50_LEVELS
+    K, L, P, A = 6, 4, 4, 10
+    C = A * P * K                                   # 240 channels, one per sample
+    shape, start, num_feat = synthetic.level_tables(sizes, K)
+    v = tie_locations(sizes, seed=3)
+    per = A * P * K * 2
+    nb = min(len(v) // per, 24)
+    loc = torch.from_numpy(v[:nb * per].copy()).reshape(nb, A, P, K, 2)
+    w = torch.zeros(nb, A, P, K, L, C)
+    go = torch.zeros(nb, A, C)
+    for a in range(A):
+        for p in range(P):
+            for k in range(K):
+                ch = (a * P + p) * K + k
+                w[:, a, p, k, :, ch] = 1.0
+                go[:, a, ch] = 1.0
+    feat = torch.ones(nb, num_feat, C)
+    sh, st = shape.int().cuda(), start.int().cuda()
+    rgf = torch.zeros(nb, num_feat, C, device="cuda")
+    rgl = torch.zeros_like(loc).cuda(); rgw = torch.zeros_like(w).cuda()
+    ref_ext.deformable_aggregation_backward(feat.cuda(), sh, st, loc.cuda(), w.cuda(), go.cuda(),
+                                            rgf, rgl, rgw)
+    touched_ref = (rgf != 0).cpu().numpy()          # [nb, num_feat, C]
+    valid, rows = cabi.debug_indices(sh, st, loc.cuda())
+    valid, rows = valid.cpu().numpy(), rows.cpu().numpy()
+    _, ov, orows = oracle.forward(np.zeros((nb, num_feat, 1), np.float32), shape, start, loc,
+                                  np.zeros((nb, A, P, K, L, 1), np.float32), side_channel=True)
+    np.testing.assert_array_equal(valid, ov)
+    np.testing.assert_array_equal(rows, orows)
+    mine = np.zeros_like(touched_ref)
+    b_idx = np.arange(nb)[:, None, None, None, None, None]
+    ch = ((np.arange(A)[:, None, None] * P + np.arange(P)[None, :, None]) * K
+          + np.arange(K)[None, None, :])[None, :, :, :, None, None]
+    sel = rows >= 0
+    mine[np.broadcast_to(b_idx, rows.shape)[sel], rows[sel], np.broadcast_to(ch, rows.shape)[sel]] = True
+    # a corner with an exactly-zero bilinear weight leaves no trace in the reference gradient:
+    # the reference pattern must be a subset of ours, and equal wherever our weight is non-zero
+    assert not (touched_ref & ~mine).any(), "reference touched a row our geometry does not"
+    gf, _, _ = cabi.backward(feat.cuda(), sh, st, loc.cuda(), w.cuda(), go.cuda())
+    np.testing.assert_array_equal((gf != 0).cpu().numpy(), touched_ref)
+    # masks: a sample is valid iff the reference produced any gradient for its channel … unless
+    # every corner weight is zero, which cannot happen for a valid sample (weights sum to 1 over
+    # in-bounds + out-of-bounds corners; at least one in-bounds corner has weight > 0)
+    ref_valid = touched_ref.any(axis=1).reshape(nb, A, P, K)
+    np.testing.assert_array_equal(ref_valid, valid.astype(bool))
