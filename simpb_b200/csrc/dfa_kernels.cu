@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "dfa_b200.h"
 
@@ -114,21 +115,50 @@ struct FeatVec;
 template <>
 struct FeatVec<float> {
   static constexpr int VEC = 4;
-  __device__ static __forceinline__ void load(const float *p, float (&v)[4]) {
-    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+  typedef float4 raw_t;
+  __device__ static __forceinline__ raw_t load_raw(const float *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+  }
+  __device__ static __forceinline__ raw_t zero_raw() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ static __forceinline__ void unpack(const raw_t &t, float (&v)[4]) {
     v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  __device__ static __forceinline__ void load(const float *p, float (&v)[4]) { unpack(load_raw(p), v); }
+  // acc += c * raw, packed FFMA2 (sm_100 fma.rn.f32x2)
+  __device__ static __forceinline__ void fma(float (&acc)[4], float c, const raw_t &t) {
+    const float2 cc = make_float2(c, c);
+    float2 a0 = __ffma2_rn(cc, make_float2(t.x, t.y), make_float2(acc[0], acc[1]));
+    float2 a1 = __ffma2_rn(cc, make_float2(t.z, t.w), make_float2(acc[2], acc[3]));
+    acc[0] = a0.x, acc[1] = a0.y, acc[2] = a1.x, acc[3] = a1.y;
   }
 };
 template <>
 struct FeatVec<__nv_bfloat16> {
   static constexpr int VEC = 8;
-  __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+  typedef uint4 raw_t;
+  __device__ static __forceinline__ raw_t load_raw(const __nv_bfloat16 *p) {
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+  }
+  __device__ static __forceinline__ raw_t zero_raw() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ static __forceinline__ void unpack(const raw_t &t, float (&v)[8]) {
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // bf16 → fp32 is a 16-bit shift
       v[2 * i] = __uint_as_float(w[i] << 16);
       v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) {
+    unpack(load_raw(p), v);
+  }
+  __device__ static __forceinline__ void fma(float (&acc)[8], float c, const raw_t &t) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+    const float2 cc = make_float2(c, c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+      const float2 a = __ffma2_rn(cc, x, make_float2(acc[2 * i], acc[2 * i + 1]));
+      acc[2 * i] = a.x, acc[2 * i + 1] = a.y;
     }
   }
 };
@@ -304,6 +334,152 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256) ? ((sizeof(T) == 4 ? 1536 
 #pragma unroll
     for (int c = 0; c < VEC / 4; ++c)
       o[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// forward, row-sliced mapping
+// ------------------------------------------------------------------------------------------
+// A feature row (C channels) is `vpr` 16-byte vectors.  The CTA is split into NT/vpr slices;
+// slice s owns taps s, s+slices, ... and inside a slice thread v owns vector v of the row, i.e.
+// VEC consecutive channels of ONE group, for all four corners of the tap.  Per tap a thread
+// issues four 128-bit loads (a warp covers 512 contiguous bytes of each corner row), reads the
+// tap record with two broadcast LDS.128 and accumulates with packed FFMA2.  Slices are folded
+// through shared memory at the end.  Compared with the one-warp-per-group mapping this needs
+// ~3.5x fewer instructions per byte gathered and shortens an anchor's serial chain by `slices`.
+struct SmemLayout2 {
+  uint32_t w, loc, off, bw, widx, list, tab, red, bar, total;
+};
+__host__ __device__ inline SmemLayout2 smem_layout2(int P, int K, int L, int G, int C, int slices,
+                                                    int tap_pad) {
+  SmemLayout2 s;
+  const uint32_t taps = align_up(static_cast<uint32_t>(P) * K * L, tap_pad) + tap_pad;
+  uint32_t o = 0;
+  s.w = o, o = align_up(o + 4u * P * K * L * G, 16);
+  s.loc = o, o = align_up(o + 8u * P * K, 16);
+  s.off = o, o = align_up(o + 16u * taps, 16);
+  s.bw = o, o = align_up(o + 16u * taps, 16);
+  s.widx = o, o = align_up(o + 4u * taps, 16);
+  s.list = o, o = align_up(o + 4u * P * K, 16);
+  s.tab = o, o = align_up(o + 12u * K * L, 16);
+  s.red = o, o = align_up(o + 4u * slices * C, 16);
+  s.bar = o, o += 32;
+  s.total = o;
+  return s;
+}
+
+template <typename T, int U, bool TMA, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+    dfa_fwd_rows_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                        const int *__restrict__ start, const float *__restrict__ loc,
+                        const float *__restrict__ weights, float *__restrict__ out, Dims d, int vpr) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int slices = NT / vpr;
+  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  uint4 *s_off = reinterpret_cast<uint4 *>(smem + lay.off);
+  float4 *s_bw = reinterpret_cast<float4 *>(smem + lay.bw);
+  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  int *s_list = reinterpret_cast<int *>(smem + lay.list);
+  int *s_tab = reinterpret_cast<int *>(smem + lay.tab);
+  float *s_red = reinterpret_cast<float *>(smem + lay.red);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+
+  const int tid = threadIdx.x;
+  const int anchor = blockIdx.x;  // b * A + a
+  const int b = anchor / d.A;
+  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
+
+  // level tables → shared memory while the TMA copies are in flight
+  for (int i = tid; i < d.K * d.L; i += NT) {
+    s_tab[3 * i] = __ldg(shape + 2 * i);
+    s_tab[3 * i + 1] = __ldg(shape + 2 * i + 1);
+    s_tab[3 * i + 2] = __ldg(start + i);
+  }
+  const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
+                                        weights + static_cast<size_t>(anchor) * wcount, s_w,
+                                        s_loc, s_list, bars, s_nvalid, PK, wcount);
+  const int ntaps = nv * d.L;
+  const int step = slices * U;
+  const int ntaps_pad = (ntaps + step - 1) / step * step;
+
+  // Tap records.  Corner offsets are BYTE offsets inside the batch item.  A corner that falls
+  // outside the map (zero padding) is redirected to an in-bounds corner of the same tap with a
+  // zero bilinear weight — a valid sample always has one — so the main loop needs no predicates
+  // (and a non-finite feature there would reach the reference's result through the in-bounds
+  // corner as well).  Padding taps replay tap 0 with zero weights.
+  for (int t = tid; t < ntaps_pad; t += NT) {
+    const int tt = t < ntaps ? t : 0;
+    const int l = tt / nv, i = tt - l * nv;  // level-major: coarse-level neighbours back to back
+    const int s = s_list[i];
+    const int kl = (s % d.K) * d.L + l;
+    TapGeom gm;
+    tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], s_tab[3 * kl], s_tab[3 * kl + 1], s_tab[3 * kl + 2],
+                 gm);
+    const int safe = gm.row[0] >= 0 ? gm.row[0] : gm.row[1] >= 0 ? gm.row[1]
+                   : gm.row[2] >= 0 ? gm.row[2] : gm.row[3];
+    const float live = t < ntaps ? 1.f : 0.f;
+    const uint32_t rb = static_cast<uint32_t>(d.C) * sizeof(T);
+    uint4 off;
+    float4 bw;
+    off.x = (gm.row[0] >= 0 ? gm.row[0] : safe) * rb, bw.x = gm.row[0] >= 0 ? live * gm.hh * gm.hw : 0.f;
+    off.y = (gm.row[1] >= 0 ? gm.row[1] : safe) * rb, bw.y = gm.row[1] >= 0 ? live * gm.hh * gm.lw : 0.f;
+    off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, bw.z = gm.row[2] >= 0 ? live * gm.lh * gm.hw : 0.f;
+    off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, bw.w = gm.row[3] >= 0 ? live * gm.lh * gm.lw : 0.f;
+    s_off[t] = off, s_bw[t] = bw, s_widx[t] = (s * d.L + l) * d.G;
+  }
+  __syncthreads();
+  if (TMA) mbar_wait(&bars[1], 0);  // weights have landed
+
+  const int slice = tid / vpr, v = tid - slice * vpr;
+  const int ch = v * VEC;
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+
+  if (slice < slices) {
+    const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
+                              static_cast<size_t>(b) * d.num_feat * d.C * sizeof(T);
+    const uint32_t lane_off = static_cast<uint32_t>(ch) * sizeof(T);
+    const float *s_wg = s_w + ch / (d.C / d.G);
+    for (int t0 = slice; t0 < ntaps_pad; t0 += step) {
+      typename FeatVec<T>::raw_t val[U][4];
+      float cw[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + u * slices;
+        const uint4 off = s_off[t];
+        val[u][0] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.x + lane_off)));
+        val[u][1] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.y + lane_off)));
+        val[u][2] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.z + lane_off)));
+        val[u][3] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.w + lane_off)));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + u * slices;
+        const float4 bw = s_bw[t];
+        const float wgt = s_wg[s_widx[t]];
+        cw[u][0] = bw.x * wgt, cw[u][1] = bw.y * wgt, cw[u][2] = bw.z * wgt, cw[u][3] = bw.w * wgt;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) FeatVec<T>::fma(acc, cw[u][q], val[u][q]);
+    }
+    float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
+#pragma unroll
+    for (int c = 0; c < VEC / 4; ++c)
+      r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+  }
+  __syncthreads();
+  for (int c = tid; c < d.C; c += NT) {
+    float sum = 0.f;
+    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
+    out[static_cast<size_t>(anchor) * d.C + c] = sum;
   }
 }
 
@@ -767,9 +943,58 @@ inline bool tma_ok(const Dims &d, const float *loc, const float *w) {
     default: return CALL(1);                      \
   }
 
+template <typename T, int U, bool TMA, int NT, int MINB>
+int launch_fwd_rows(const void *feat, const int *shape, const int *start, const float *loc,
+                    const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
+  auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB>;
+  const int slices = NT / vpr;
+  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  kern<<<d.bs * d.A, NT, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w, out, d,
+                                          vpr);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Row-sliced fast path: the row is a power-of-two number of 16-byte vectors (<= block size) and
+// every vector lies inside one channel group.
+template <typename T>
+int rows_vpr(const Dims &d, const void *feat, int nt) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  if (d.C % VEC != 0 || (d.C / d.G) % VEC != 0 || !aligned(feat, 16)) return 0;
+  const int vpr = d.C / VEC;
+  if (vpr > nt || (vpr & (vpr - 1)) != 0) return 0;
+  if (static_cast<long long>(d.num_feat) * d.C * static_cast<long long>(sizeof(T)) >= (1ll << 32)) return 0;
+  return vpr;
+}
+
+inline int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <typename T>
 int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
                   const float *w, float *out, const Dims &d, cudaStream_t st) {
+  // DFA_FWD_VARIANT (tuning knob): 0 = one-warp-per-group kernel, 1..4 = row-sliced kernel with
+  // (threads, taps in flight) = (256,1) (256,2) (512,1) (512,2)
+  const int variant = env_int("DFA_FWD_VARIANT", 1);
+  if (variant >= 1) {
+    const int nt = variant >= 3 ? 512 : 256;
+    const int vpr = rows_vpr<T>(d, feat, nt);
+    if (vpr) {
+      const bool tma = tma_ok(d, loc, w);
+#define ROWS(U, NT, MINB)                                                                        \
+  (tma ? launch_fwd_rows<T, U, true, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st)      \
+       : launch_fwd_rows<T, U, false, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st))
+      switch (variant) {
+        case 1: return ROWS(1, 256, 6);
+        case 2: return ROWS(2, 256, 4);
+        case 3: return ROWS(1, 512, 3);
+        default: return ROWS(2, 512, 2);
+      }
+#undef ROWS
+    }
+  }
   const int lpg = fast_lpg<T>(d, feat);
   if (lpg && aligned(out, 16)) {
     const bool tma = tma_ok(d, loc, w);
