@@ -69,6 +69,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// TMA bulk prefetch of `bytes` (multiple of 16) into L2: no registers, no shared memory.
+__device__ __forceinline__ void tma_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
                "f"(d)
@@ -369,14 +373,16 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int P, int K, int L, int G, 
   return s;
 }
 
-template <typename T, int U, bool TMA, int NT, int MINB>
+template <typename T, int U, bool TMA, int NT, int MINB, bool PF>
 __global__ void __launch_bounds__(NT, MINB)
     dfa_fwd_rows_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
                         const int *__restrict__ start, const float *__restrict__ loc,
-                        const float *__restrict__ weights, float *__restrict__ out, Dims d, int vpr) {
+                        const float *__restrict__ weights, float *__restrict__ out, Dims d,
+                        int vpr_log2) {
   constexpr int VEC = FeatVec<T>::VEC;
   extern __shared__ __align__(128) unsigned char smem[];
-  const int slices = NT / vpr;
+  const int vpr = 1 << vpr_log2;
+  const int slices = NT >> vpr_log2;
   const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
   float *s_w = reinterpret_cast<float *>(smem + lay.w);
   float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
@@ -431,11 +437,20 @@ __global__ void __launch_bounds__(NT, MINB)
     off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, bw.z = gm.row[2] >= 0 ? live * gm.lh * gm.hw : 0.f;
     off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, bw.w = gm.row[3] >= 0 ? live * gm.lh * gm.lw : 0.f;
     s_off[t] = off, s_bw[t] = bw, s_widx[t] = (s * d.L + l) * d.G;
+    if (PF && t < ntaps) {
+      // start the rows' DRAM → L2 transfers now, long before the first register load needs them
+      const unsigned char *fr = reinterpret_cast<const unsigned char *>(feat) +
+                                static_cast<size_t>(b) * d.num_feat * rb;
+      if (gm.row[0] >= 0) tma_prefetch_l2(fr + off.x, rb);
+      if (gm.row[1] >= 0) tma_prefetch_l2(fr + off.y, rb);
+      if (gm.row[2] >= 0) tma_prefetch_l2(fr + off.z, rb);
+      if (gm.row[3] >= 0) tma_prefetch_l2(fr + off.w, rb);
+    }
   }
   __syncthreads();
   if (TMA) mbar_wait(&bars[1], 0);  // weights have landed
 
-  const int slice = tid / vpr, v = tid - slice * vpr;
+  const int slice = tid >> vpr_log2, v = tid & (vpr - 1);
   const int ch = v * VEC;
   float acc[VEC];
 #pragma unroll
@@ -470,6 +485,217 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
         for (int q = 0; q < 4; ++q) FeatVec<T>::fma(acc, cw[u][q], val[u][q]);
     }
+    float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
+#pragma unroll
+    for (int c = 0; c < VEC / 4; ++c)
+      r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+  }
+  __syncthreads();
+  for (int c = tid; c < d.C; c += NT) {
+    float sum = 0.f;
+    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
+    out[static_cast<size_t>(anchor) * d.C + c] = sum;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// forward, row-deduplicated
+// ------------------------------------------------------------------------------------------
+// The key points of one anchor project close together, so at the coarse levels most of their
+// bilinear corners name the SAME feature rows (rig inputs: 230 corner references per anchor, 106
+// distinct rows).  Per chunk of taps the CTA therefore
+//   A. inserts every in-bounds corner's row into a small shared-memory hash table (atomicCAS);
+//      the inserting thread gives a new row its dense index and records its byte offset,
+//   B. folds bilinear weight x group weight of every reference into coef[row][group]
+//      (shared-memory float atomics),
+//   C. gathers each DISTINCT row once: thread = one 16-byte vector of the row (a warp covers 512
+//      contiguous bytes), U rows in flight per thread, acc += coef[row][group(thread)] * row.
+// Slices of the CTA (NT / vectors-per-row) take rows round-robin and are folded through shared
+// memory at the end.  Compared with gathering per tap this halves L1 wavefronts, L2 requests,
+// FMAs and loop instructions on SimPB-like geometry, and costs nothing extra in HBM traffic.
+// The summation order follows the hash insertion order, so the result is reproducible only to
+// rounding (~1e-7 relative) — like the reference, which accumulates with float atomics.
+struct SmemLayout3 {
+  uint32_t w, loc, list, tab, key, head, rowoff, rowslot, coef, refnext, refbw, refw, red, bar, total;
+  uint32_t hsize, hbits;
+};
+__host__ __device__ inline SmemLayout3 smem_layout3(int P, int K, int L, int G, int C, int slices,
+                                                    int chunk_taps, int U) {
+  SmemLayout3 s;
+  const uint32_t rows_cap = 4u * chunk_taps;
+  s.hsize = 1, s.hbits = 0;
+  while (s.hsize < 2 * rows_cap) s.hsize <<= 1, ++s.hbits;
+  const uint32_t rows_pad = rows_cap + static_cast<uint32_t>(slices) * U;
+  uint32_t o = 0;
+  s.w = o, o = align_up(o + 4u * P * K * L * G, 16);
+  s.loc = o, o = align_up(o + 8u * P * K, 16);
+  s.list = o, o = align_up(o + 4u * P * K, 16);
+  s.tab = o, o = align_up(o + 12u * K * L, 16);
+  s.key = o, o = align_up(o + 4u * s.hsize, 16);
+  s.head = o, o = align_up(o + 4u * s.hsize, 16);
+  s.rowoff = o, o = align_up(o + 4u * rows_pad, 16);
+  s.rowslot = o, o = align_up(o + 4u * rows_cap, 16);
+  s.coef = o, o = align_up(o + 4u * rows_pad * G, 16);
+  s.refnext = o, o = align_up(o + 4u * rows_cap, 16);
+  s.refbw = o, o = align_up(o + 4u * rows_cap, 16);
+  s.refw = o, o = align_up(o + 4u * chunk_taps, 16);
+  s.red = o, o = align_up(o + 4u * slices * C, 16);
+  s.bar = o, o += 32;
+  s.total = o;
+  return s;
+}
+
+struct DedupArgs {  // host-computed, so no thread spends instructions deriving them
+  int vpr_log2, chunk_taps, hbits;
+  SmemLayout3 lay;
+};
+
+template <typename T, int U, bool TMA, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+    dfa_fwd_dedup_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                         const int *__restrict__ start, const float *__restrict__ loc,
+                         const float *__restrict__ weights, float *__restrict__ out, Dims d,
+                         DedupArgs a) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int vpr = 1 << a.vpr_log2;
+  const int slices = NT >> a.vpr_log2;
+  float *s_w = reinterpret_cast<float *>(smem + a.lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + a.lay.loc);
+  int *s_list = reinterpret_cast<int *>(smem + a.lay.list);
+  int *s_tab = reinterpret_cast<int *>(smem + a.lay.tab);
+  int *s_key = reinterpret_cast<int *>(smem + a.lay.key);
+  int *s_head = reinterpret_cast<int *>(smem + a.lay.head);
+  uint32_t *s_rowoff = reinterpret_cast<uint32_t *>(smem + a.lay.rowoff);
+  int *s_rowslot = reinterpret_cast<int *>(smem + a.lay.rowslot);
+  float *s_coef = reinterpret_cast<float *>(smem + a.lay.coef);
+  int *s_refnext = reinterpret_cast<int *>(smem + a.lay.refnext);
+  float *s_refbw = reinterpret_cast<float *>(smem + a.lay.refbw);
+  int *s_refw = reinterpret_cast<int *>(smem + a.lay.refw);
+  float *s_red = reinterpret_cast<float *>(smem + a.lay.red);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+  int *s_nrows = s_nvalid + 1;
+
+  const int tid = threadIdx.x;
+  const int anchor = blockIdx.x;  // b * A + a
+  const int b = anchor / d.A;
+  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
+  const int hsize = static_cast<int>(a.lay.hsize), hmask = hsize - 1;
+  const uint32_t rb = static_cast<uint32_t>(d.C) * sizeof(T);  // bytes per feature row
+
+  // level tables and an empty hash table while the TMA copies are in flight
+  for (int i = tid; i < d.K * d.L; i += NT) {
+    s_tab[3 * i] = __ldg(shape + 2 * i);
+    s_tab[3 * i + 1] = __ldg(shape + 2 * i + 1);
+    s_tab[3 * i + 2] = __ldg(start + i);
+  }
+  for (int i = tid; i < hsize; i += NT) s_key[i] = -1, s_head[i] = -1;
+  if (tid == 0) *s_nrows = 0;
+  const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
+                                        weights + static_cast<size_t>(anchor) * wcount, s_w,
+                                        s_loc, s_list, bars, s_nvalid, PK, wcount);
+  const int ntaps = nv * d.L;
+
+  const int slice = tid >> a.vpr_log2, v = tid & (vpr - 1);
+  const int ch = v * VEC;
+  const int g = ch / (d.C / d.G);
+  const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
+                            static_cast<size_t>(b) * d.num_feat * rb + static_cast<uint32_t>(ch) * sizeof(T);
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+  bool weights_ready = !TMA;
+  const int step = slices * U;
+  const int gq = (d.G + 3) >> 2;  // group quads per row
+
+  for (int c0 = 0; c0 < ntaps; c0 += a.chunk_taps) {
+    const int nt = min(a.chunk_taps, ntaps - c0);
+    // ---- A: geometry, hash insertion and reference lists — one thread per tap
+    if (tid < nt) {
+      const int t = c0 + tid;
+      const int l = t / nv, i = t - l * nv;  // level-major: same-level neighbours share a chunk
+      const int s = s_list[i];
+      const int kl = (s % d.K) * d.L + l;
+      TapGeom gm;
+      tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], s_tab[3 * kl], s_tab[3 * kl + 1], s_tab[3 * kl + 2],
+                   gm);
+      const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
+      s_refw[tid] = (s * d.L + l) * d.G;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (gm.row[q] < 0) continue;  // outside the map: zero padding, no reference
+        const int key = gm.row[q];
+        int slot = static_cast<int>((static_cast<uint32_t>(key) * 2654435761u) >> (32 - a.hbits));
+        while (true) {
+          const int old = atomicCAS(&s_key[slot], -1, key);
+          if (old == -1) {  // first reference to this row: give it the next dense index
+            const int j = atomicAdd(s_nrows, 1);
+            s_rowoff[j] = static_cast<uint32_t>(key) * rb;
+            s_rowslot[j] = slot;
+            break;
+          }
+          if (old == key) break;
+          slot = (slot + 1) & hmask;
+        }
+        const int ref = 4 * tid + q;
+        s_refbw[ref] = bw[q];
+        s_refnext[ref] = atomicExch(&s_head[slot], ref);  // push onto the row's reference list
+      }
+    }
+    __syncthreads();
+    if (!weights_ready) {
+      mbar_wait(&bars[1], 0);  // weights have landed
+      weights_ready = true;
+    }
+    // ---- B: coef[row][group] = sum over the row's references of bilinear weight x group weight
+    //         (owner computes: one thread per row and group quad walks the list; no float atomics)
+    const int nrows = *s_nrows;
+    const int nrows_pad = (nrows + step - 1) / step * step;
+    for (int item = tid; item < nrows_pad * gq; item += NT) {
+      const int j = item / gq, g0 = (item - j * gq) * 4;
+      float c4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j < nrows) {
+        for (int ref = s_head[s_rowslot[j]]; ref >= 0; ref = s_refnext[ref]) {
+          const float bwv = s_refbw[ref];
+          const float *wp = s_w + s_refw[ref >> 2] + g0;
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            if (g0 + x < d.G) c4[x] = fmaf(bwv, wp[x], c4[x]);
+        }
+      } else if (g0 == 0) {
+        s_rowoff[j] = s_rowoff[0];  // padding rows replay row 0 with zero coefficients
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        if (g0 + x < d.G) s_coef[j * d.G + g0 + x] = c4[x];
+    }
+    __syncthreads();
+    // ---- C: gather every distinct row once
+    if (slice < slices) {
+      for (int j0 = slice; j0 < nrows_pad; j0 += step) {
+        typename FeatVec<T>::raw_t val[U];
+        float cf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          val[u] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + s_rowoff[j0 + u * slices]));
+#pragma unroll
+        for (int u = 0; u < U; ++u) cf[u] = s_coef[(j0 + u * slices) * d.G + g];
+#pragma unroll
+        for (int u = 0; u < U; ++u) FeatVec<T>::fma(acc, cf[u], val[u]);
+      }
+    }
+    if (c0 + a.chunk_taps < ntaps) {  // more chunks: recycle the table
+      __syncthreads();
+      for (int i = tid; i < hsize; i += NT) s_key[i] = -1, s_head[i] = -1;
+      if (tid == 0) *s_nrows = 0;
+      __syncthreads();
+    }
+  }
+  if (TMA && !weights_ready) mbar_wait(&bars[1], 0);  // never leave with a copy in flight
+
+  if (slice < slices) {
     float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
 #pragma unroll
     for (int c = 0; c < VEC / 4; ++c)
@@ -943,15 +1169,17 @@ inline bool tma_ok(const Dims &d, const float *loc, const float *w) {
     default: return CALL(1);                      \
   }
 
-template <typename T, int U, bool TMA, int NT, int MINB>
+template <typename T, int U, bool TMA, int NT, int MINB, bool PF>
 int launch_fwd_rows(const void *feat, const int *shape, const int *start, const float *loc,
                     const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
-  auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB>;
+  auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB, PF>;
   const int slices = NT / vpr;
+  int vpr_log2 = 0;
+  while ((1 << vpr_log2) < vpr) ++vpr_log2;
   const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
   if (int rc = set_smem(kern, lay.total)) return rc;
   kern<<<d.bs * d.A, NT, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w, out, d,
-                                          vpr);
+                                          vpr_log2);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -972,20 +1200,51 @@ inline int env_int(const char *name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+template <typename T, int U, bool TMA, int NT, int MINB>
+int launch_fwd_dedup(const void *feat, const int *shape, const int *start, const float *loc,
+                     const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
+  auto kern = dfa_fwd_dedup_kernel<T, U, TMA, NT, MINB>;
+  const int slices = NT / vpr;
+  DedupArgs a;
+  a.vpr_log2 = 0;
+  while ((1 << a.vpr_log2) < vpr) ++a.vpr_log2;
+  // taps per chunk: one thread per tap, and coef[4*chunk][G] kept near 8 KB
+  a.chunk_taps = 64;
+  while (a.chunk_taps > 8 && 4 * a.chunk_taps * d.G * 4 > 8192) a.chunk_taps >>= 1;
+  a.lay = smem_layout3(d.P, d.K, d.L, d.G, d.C, slices, a.chunk_taps, U);
+  a.hbits = static_cast<int>(a.lay.hbits);
+  if (int rc = set_smem(kern, a.lay.total)) return rc;
+  kern<<<d.bs * d.A, NT, a.lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w, out,
+                                            d, a);
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <typename T>
 int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
                   const float *w, float *out, const Dims &d, cudaStream_t st) {
   // DFA_FWD_VARIANT (tuning knob): 0 = one-warp-per-group kernel, 1..4 = row-sliced kernel with
   // (threads, taps in flight) = (256,1) (256,2) (512,1) (512,2)
-  const int variant = env_int("DFA_FWD_VARIANT", 1);
-  if (variant >= 1) {
+  const int variant = env_int("DFA_FWD_VARIANT", 5);
+  if (variant >= 5) {  // 5, 6: row-deduplicated kernel with 4 / 8 rows in flight per thread
+    const int vpr = rows_vpr<T>(d, feat, 256);
+    if (vpr) {
+      const bool tma = tma_ok(d, loc, w);
+      if (variant == 5)
+        return tma ? launch_fwd_dedup<T, 4, true, 256, 6>(feat, shape, start, loc, w, out, d, vpr, st)
+                   : launch_fwd_dedup<T, 4, false, 256, 6>(feat, shape, start, loc, w, out, d, vpr, st);
+      return tma ? launch_fwd_dedup<T, 8, true, 256, 4>(feat, shape, start, loc, w, out, d, vpr, st)
+                 : launch_fwd_dedup<T, 8, false, 256, 4>(feat, shape, start, loc, w, out, d, vpr, st);
+    }
+  } else if (variant >= 1) {
     const int nt = variant >= 3 ? 512 : 256;
     const int vpr = rows_vpr<T>(d, feat, nt);
     if (vpr) {
       const bool tma = tma_ok(d, loc, w);
-#define ROWS(U, NT, MINB)                                                                        \
-  (tma ? launch_fwd_rows<T, U, true, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st)      \
-       : launch_fwd_rows<T, U, false, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st))
+      const bool pf = env_int("DFA_FWD_PREFETCH", 1) != 0;
+#define ROWS(U, NT, MINB)                                                                              \
+  (tma ? (pf ? launch_fwd_rows<T, U, true, NT, MINB, true>(feat, shape, start, loc, w, out, d, vpr, st)  \
+             : launch_fwd_rows<T, U, true, NT, MINB, false>(feat, shape, start, loc, w, out, d, vpr, st)) \
+       : launch_fwd_rows<T, U, false, NT, MINB, false>(feat, shape, start, loc, w, out, d, vpr, st))
       switch (variant) {
         case 1: return ROWS(1, 256, 6);
         case 2: return ROWS(2, 256, 4);

@@ -17,8 +17,9 @@ for inputs, batch, dt in cases:
     sets = [bench.to_device(maker(bs=batch, seed=s), dtype) for s in range(n_sets)]
     outs = [torch.empty(batch, 900, 256, device="cuda") for _ in sets]
     ref = None
-    for v in variants:
+    for v, pf in [(v, pf) for v in variants for pf in ((0, 1) if v > 0 else (0,))]:
         os.environ["DFA_FWD_VARIANT"] = str(v)
+        os.environ["DFA_FWD_PREFETCH"] = str(pf)
         fns = [(lambda g=g, o=o: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o))
                for g, o in zip(sets, outs)]
         ms = bench.time_graph(fns, 200, 20, True, torch.cuda.synchronize) / 200
@@ -26,5 +27,5 @@ for inputs, batch, dt in cases:
         if ref is None:
             ref = cur
         err = float((cur - ref).abs().max() / ref.abs().max())
-        print("%-8s bs=%d %-4s variant=%d  %8.2f us   (max rel diff vs first variant %.1e)"
-              % (inputs, batch, dt, v, ms * 1e3, err), flush=True)
+        print("%-8s bs=%d %-4s variant=%d pf=%d  %8.2f us   (max rel diff vs first variant %.1e)"
+              % (inputs, batch, dt, v, pf, ms * 1e3, err), flush=True)
