@@ -53,6 +53,18 @@ def parse():
 
 
 # ----------------------------------------------------------------------------- helpers
+def measured_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, taken from the
+    committed ncu capture of this exact workload (profiles/traffic.json); None if never captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    key = "%s:%s:%s:bs%d:A%d" % (args.workload, args.dtype, args.inputs, args.batch, args.anchors)
+    if os.path.exists(p):
+        t = json.load(open(p)).get(key)
+        if t:
+            return t["dram_bytes_read"] + t["dram_bytes_write"], t["kernel"]
+    return None, None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,8 +315,10 @@ def run_own_arm(args):
         if args.workload == "fwd":
             ach = b_alg / (ms_step * 1e-3) / 1e9
             achf = b_full / (ms_step * 1e-3) / 1e9
+            traffic, kname = measured_traffic(args)
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "kernel": "dfa_fwd_kernel", "kernel_us": ms_step * 1e3,
+                    "traffic": traffic, "kernel": kname or "dfa_fwd_rows_kernel",
+                    "kernel_us": ms_step * 1e3,
                     "algorithmic_bytes": b_alg, "distinct_rows": sum(u) / len(u),
                     "peak_source": peak_src,
                     "whole_pyramid_variant": {"bytes": b_full, "achieved": achf, "frac": achf / peak}}

@@ -16,6 +16,10 @@
  *   dfa_backward           ops/src/deformable_aggregation_cuda.cu:291-318  (deformable_aggregation_grad)
  *   dfa_flatten_maps       ops/__init__.py:63-92                           (feature_maps_format)
  *   dfa_keypoints_project  models/detection3d/blocks.py:181-207 + models/blocks.py:198-213
+ *   dfa_keypoints_project_backward   autograd of the two above (torch ops in the reference)
+ *   dfa_softmax_weights    models/blocks.py:175-195 (softmax over cams x levels x points, attn-drop
+ *                          mask) + the permute of models/blocks.py:133-144
+ *   dfa_softmax_weights_backward     autograd of the above
  *   dfa_forward_host       the same forward, called with HOST buffers (copies inside)
  *
  * Tensor layouts (row-major, innermost last) — ops/src/deformable_aggregation.cpp:22-28:
@@ -105,6 +109,27 @@ int dfa_keypoints_project(const float *anchor, const float *fix_scale, int num_f
                           const float *learnable_logits, const float *projection_mat,
                           const float *image_wh, float *key_points, float *sampling_location,
                           int bs, int num_anchors, int num_pts, int num_cams, void *stream);
+
+/* Gradients of dfa_keypoints_project wrt the anchor ([bs,A,11]; velocity entries get 0) and the
+ * learnable-offset logits ([bs,A,(P-F)*3], may be NULL), given grad_sampling_location
+ * [bs,A,P,K,2].  Both outputs are fully written (no zero-fill needed). */
+int dfa_keypoints_project_backward(const float *anchor, const float *fix_scale, int num_fix,
+                                   const float *learnable_logits, const float *projection_mat,
+                                   const float *image_wh, const float *grad_sampling_location,
+                                   float *grad_anchor, float *grad_learnable_logits, int bs,
+                                   int num_anchors, int num_pts, int num_cams, void *stream);
+
+/* Attention weights of the module: logits [bs,A,K,L,P,G] (the weights_fc output, any view of that
+ * memory order) -> weights [bs,A,P,K,L,G] = softmax over the K*L*P entries of every (b,a,g),
+ * times keep_mask[b,a,k,p] * scale when keep_mask (uint8 [bs,A,K,P]) is given (training-time
+ * attn-drop, scale = 1/(1-p)).  Needs 256 % G == 0. */
+int dfa_softmax_weights(const float *logits, const uint8_t *keep_mask, float scale, float *weights,
+                        int bs, int num_anchors, int num_cams, int num_scale, int num_pts,
+                        int num_groups, void *stream);
+int dfa_softmax_weights_backward(const float *logits, const uint8_t *keep_mask, float scale,
+                                 const float *grad_weights, float *grad_logits, int bs,
+                                 int num_anchors, int num_cams, int num_scale, int num_pts,
+                                 int num_groups, void *stream);
 
 /* Forward with HOST buffers: host→device copies of all five inputs, the kernel, and the
  * device→host copy of the output, on `stream`, then a stream synchronise.  Host buffers should

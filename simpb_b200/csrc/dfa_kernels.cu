@@ -500,213 +500,390 @@ __global__ void __launch_bounds__(NT, MINB)
 
 
 // ------------------------------------------------------------------------------------------
-// forward, row-deduplicated
+// forward with row merging and a balanced gather (the default for SimPB's shapes)
 // ------------------------------------------------------------------------------------------
-// The key points of one anchor project close together, so at the coarse levels most of their
-// bilinear corners name the SAME feature rows (rig inputs: 230 corner references per anchor, 106
-// distinct rows).  Per chunk of taps the CTA therefore
-//   A. inserts every in-bounds corner's row into a small shared-memory hash table (atomicCAS);
-//      the inserting thread gives a new row its dense index and records its byte offset,
-//   B. folds bilinear weight x group weight of every reference into coef[row][group]
-//      (shared-memory float atomics),
-//   C. gathers each DISTINCT row once: thread = one 16-byte vector of the row (a warp covers 512
-//      contiguous bytes), U rows in flight per thread, acc += coef[row][group(thread)] * row.
-// Slices of the CTA (NT / vectors-per-row) take rows round-robin and are folded through shared
-// memory at the end.  Compared with gathering per tap this halves L1 wavefronts, L2 requests,
-// FMAs and loop instructions on SimPB-like geometry, and costs nothing extra in HBM traffic.
-// The summation order follows the hash insertion order, so the result is reproducible only to
-// rounding (~1e-7 relative) — like the reference, which accumulates with float atomics.
-struct SmemLayout3 {
-  uint32_t w, loc, list, tab, key, head, rowoff, rowslot, coef, refnext, refbw, refw, red, bar, total;
-  uint32_t hsize, hbits;
+// What bounds the gather on B200 is not HBM but the SM's load path — every 128 bytes a warp pulls
+// into registers is one L1 wavefront, hit or miss (ncu: l1tex data pipe 71 % busy on the
+// row-sliced kernel while DRAM sits at 34 %) — and, at one batch item, the length of each warp's
+// dependent chain.  So this kernel pulls fewer rows and keeps every warp's loads independent.
+// The key points of one anchor project close together: at the coarse levels their bilinear
+// corners name the same feature rows again and again (camera-rig inputs: 230 corner references
+// per anchor, 106 distinct rows).  They are merged without sorting or atomics:
+//
+//   prologue (warp 0)  the anchor's sampling locations arrive by one TMA bulk copy; the warp
+//                      compacts the samples that pass the op's (0,1) test and issues the weights
+//                      as TMA bulk copies too — one 128-byte line per VALID sample when the anchor
+//                      is sparse (a sample's L*G weights are contiguous), the whole block when it
+//                      is dense or when the grid is so small that latency, not bandwidth, rules.
+//   merge              warp l owns level l.  A chunk = up to 8 valid samples = 32 corner references,
+//                      one per lane.  __match_any_sync groups lanes that name the same row; the
+//                      lowest lane of each group sums the group's (bilinear weight x group weight)
+//                      coefficients with shuffles in ascending lane order.  Across the chunks of
+//                      the level a small direct-mapped table (row -> slot) in shared memory lets a
+//                      leader find a row an earlier chunk already listed and add to its
+//                      coefficients instead.  Result: a list of (row offset, coef[G]) per warp.
+//   gather             after one barrier every warp takes the same share of every list (slot p of
+//                      list c goes to warp (p + c) mod NW), so the warps finish together.  A lane
+//                      owns VPL 16-byte vectors of a row: one warp instruction covers 512 contiguous
+//                      bytes, U rows are in flight per lane, and the weighted sum stays in
+//                      registers (packed FFMA2).
+//   epilogue           the warps' partial rows are folded through shared memory and the anchor's
+//                      output row is written once.
+//
+// Merge and summation order are fixed, so results are bitwise reproducible.
+#ifdef DFA_PHASE_TIMING
+// Tool-only build (tools/phase_timing.py): per-warp clock64() stamps at the phase boundaries of the
+// merging forward kernel, written to a caller-provided buffer [anchor][warp][8].
+__device__ long long *g_phase_buf = nullptr;
+#define DFA_STAMP(i)                                                                      \
+  do {                                                                                    \
+    if (g_phase_buf && lane == 0)                                                         \
+      g_phase_buf[(static_cast<size_t>(blockIdx.x) * NW + warp) * 8 + (i)] = clock64();   \
+  } while (0)
+#else
+#define DFA_STAMP(i) do {} while (0)
+#endif
+
+constexpr int MERGE_CAP = 64;     // slots per warp list and round (two chunks)
+constexpr int MERGE_TABLE = 128;  // entries of a warp's row -> slot table
+constexpr int MERGE_WPAD = 8;     // floats between the weight lines of a sparse anchor (bank spread)
+
+struct MergeLayout {
+  uint32_t w, loc, list, tab, rowoff, coef, table, cnt, mine_off, mine_slot, mine_stride, bar, total;
 };
-__host__ __device__ inline SmemLayout3 smem_layout3(int P, int K, int L, int G, int C, int slices,
-                                                    int chunk_taps, int U) {
-  SmemLayout3 s;
-  const uint32_t rows_cap = 4u * chunk_taps;
-  s.hsize = 1, s.hbits = 0;
-  while (s.hsize < 2 * rows_cap) s.hsize <<= 1, ++s.hbits;
-  const uint32_t rows_pad = rows_cap + static_cast<uint32_t>(slices) * U;
+__host__ __device__ inline MergeLayout merge_layout(int P, int K, int L, int G, int NW, int U) {
+  MergeLayout s;
+  const uint32_t slots = static_cast<uint32_t>(NW) * MERGE_CAP;
   uint32_t o = 0;
-  s.w = o, o = align_up(o + 4u * P * K * L * G, 16);
+  s.w = o, o = align_up(o + 4u * P * K * L * G, 128);
   s.loc = o, o = align_up(o + 8u * P * K, 16);
   s.list = o, o = align_up(o + 4u * P * K, 16);
-  s.tab = o, o = align_up(o + 12u * K * L, 16);
-  s.key = o, o = align_up(o + 4u * s.hsize, 16);
-  s.head = o, o = align_up(o + 4u * s.hsize, 16);
-  s.rowoff = o, o = align_up(o + 4u * rows_pad, 16);
-  s.rowslot = o, o = align_up(o + 4u * rows_cap, 16);
-  s.coef = o, o = align_up(o + 4u * rows_pad * G, 16);
-  s.refnext = o, o = align_up(o + 4u * rows_cap, 16);
-  s.refbw = o, o = align_up(o + 4u * rows_cap, 16);
-  s.refw = o, o = align_up(o + 4u * chunk_taps, 16);
-  s.red = o, o = align_up(o + 4u * slices * C, 16);
+  s.tab = o, o = align_up(o + 16u * K * L, 128);
+  s.rowoff = o, o = align_up(o + 4u * slots, 128);
+  s.coef = o, o = align_up(o + 4u * G * slots, 128);  // reused for the NW partial rows
+  s.table = o, o = align_up(o + 4u * MERGE_TABLE * NW, 128);
+  s.cnt = o, o = align_up(o + 4u * NW, 16);
+  s.mine_stride = MERGE_CAP + U;  // entries per warp (a warp's share of NW lists, padded to U)
+  s.mine_off = o, o = align_up(o + 4u * s.mine_stride * NW, 16);
+  s.mine_slot = o, o = align_up(o + 2u * s.mine_stride * NW, 16);
   s.bar = o, o += 32;
   s.total = o;
   return s;
 }
 
-struct DedupArgs {  // host-computed, so no thread spends instructions deriving them
-  int vpr_log2, chunk_taps, hbits;
-  SmemLayout3 lay;
-};
-
-template <typename T, int U, bool TMA, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-    dfa_fwd_dedup_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+// T: feature type.  VPL: 16-byte vectors per lane per row (row bytes = 512 * VPL).  G: groups.
+// NW: warps per CTA.  U: rows in flight per lane.
+template <typename T, int VPL, int G, int NW, int U, bool TMA, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+    dfa_fwd_merge_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
                          const int *__restrict__ start, const float *__restrict__ loc,
                          const float *__restrict__ weights, float *__restrict__ out, Dims d,
-                         DedupArgs a) {
+                         MergeLayout lay, int whole_weights, int prefetch) {
   constexpr int VEC = FeatVec<T>::VEC;
+  constexpr int NT = NW * 32;
+  constexpr int GPV = G / VPL;  // groups covered by one 512-byte segment of the row
+  constexpr int C = 32 * VPL * VEC;
+  static_assert(G % 4 == 0 && G % VPL == 0 && (32 * VPL) % G == 0,
+                "a 16-byte vector must lie inside one group");
+  static_assert((NW & (NW - 1)) == 0 && NW >= 2 && NW <= 32, "warps per CTA: a power of two");
+  static_assert(MERGE_CAP * G >= C, "partial rows must fit the coefficient lists");
+  static_assert(U == 2 || U == 4, "row offsets / slots of a batch are read with one vector load");
   extern __shared__ __align__(128) unsigned char smem[];
-  const int vpr = 1 << a.vpr_log2;
-  const int slices = NT >> a.vpr_log2;
-  float *s_w = reinterpret_cast<float *>(smem + a.lay.w);
-  float *s_loc = reinterpret_cast<float *>(smem + a.lay.loc);
-  int *s_list = reinterpret_cast<int *>(smem + a.lay.list);
-  int *s_tab = reinterpret_cast<int *>(smem + a.lay.tab);
-  int *s_key = reinterpret_cast<int *>(smem + a.lay.key);
-  int *s_head = reinterpret_cast<int *>(smem + a.lay.head);
-  uint32_t *s_rowoff = reinterpret_cast<uint32_t *>(smem + a.lay.rowoff);
-  int *s_rowslot = reinterpret_cast<int *>(smem + a.lay.rowslot);
-  float *s_coef = reinterpret_cast<float *>(smem + a.lay.coef);
-  int *s_refnext = reinterpret_cast<int *>(smem + a.lay.refnext);
-  float *s_refbw = reinterpret_cast<float *>(smem + a.lay.refbw);
-  int *s_refw = reinterpret_cast<int *>(smem + a.lay.refw);
-  float *s_red = reinterpret_cast<float *>(smem + a.lay.red);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + a.lay.bar);
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  uint32_t *s_list = reinterpret_cast<uint32_t *>(smem + lay.list);
+  int4 *s_tab = reinterpret_cast<int4 *>(smem + lay.tab);
+  uint32_t *s_rowoff = reinterpret_cast<uint32_t *>(smem + lay.rowoff);
+  float *s_coef = reinterpret_cast<float *>(smem + lay.coef);
+  int *s_cnt = reinterpret_cast<int *>(smem + lay.cnt);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
   int *s_nvalid = reinterpret_cast<int *>(bars + 2);
-  int *s_nrows = s_nvalid + 1;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int anchor = blockIdx.x;  // b * A + a
   const int b = anchor / d.A;
-  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
-  const int hsize = static_cast<int>(a.lay.hsize), hmask = hsize - 1;
-  const uint32_t rb = static_cast<uint32_t>(d.C) * sizeof(T);  // bytes per feature row
+  const int PK = d.P * d.K, LG = d.L * G, wcount = PK * LG;
+  const float *loc_g = loc + static_cast<size_t>(anchor) * PK * 2;
+  const float *w_g = weights + static_cast<size_t>(anchor) * wcount;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
-  // level tables and an empty hash table while the TMA copies are in flight
-  for (int i = tid; i < d.K * d.L; i += NT) {
-    s_tab[3 * i] = __ldg(shape + 2 * i);
-    s_tab[3 * i + 1] = __ldg(shape + 2 * i + 1);
-    s_tab[3 * i + 2] = __ldg(start + i);
+  // ---- prologue ------------------------------------------------------------------------------
+  DFA_STAMP(0);
+  if (TMA) {
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&bars[0], 8u * PK);
+        tma_bulk_g2s(s_loc, loc_g, 8u * PK, &bars[0]);
+        if (whole_weights) {
+          mbar_expect_tx(&bars[1], 4u * wcount);
+          tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
+        }
+      }
+      __syncwarp();
+      if (NW == 1)
+        for (int i = lane; i < d.K * d.L; i += 32)
+          s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
+      mbar_wait(&bars[0], 0);
+    } else {
+      for (int i = tid - 32; i < d.K * d.L; i += NT - 32)
+        s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
+    }
+  } else {
+    for (int i = tid; i < 2 * PK; i += NT) s_loc[i] = __ldg(loc_g + i);
+    for (int i = tid; i < d.K * d.L; i += NT)
+      s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
+    __syncthreads();
   }
-  for (int i = tid; i < hsize; i += NT) s_key[i] = -1, s_head[i] = -1;
-  if (tid == 0) *s_nrows = 0;
-  const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
-                                        weights + static_cast<size_t>(anchor) * wcount, s_w,
-                                        s_loc, s_list, bars, s_nvalid, PK, wcount);
-  const int ntaps = nv * d.L;
+  DFA_STAMP(1);
+  bool sparse_w = false;  // weight lines packed by valid-sample index (stride LG + MERGE_WPAD)
+  if (warp == 0) {
+    // compaction: entry = sample | camera << 16, in sample order
+    const float rK = 1.0f / static_cast<float>(d.K);
+    int n = 0;
+    for (int base = 0; base < PK; base += 32) {
+      const int s = base + lane;
+      bool v = false;
+      if (s < PK) {
+        const float2 xy = *reinterpret_cast<const float2 *>(s_loc + 2 * s);
+        v = sample_valid(xy.x, xy.y);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, v);
+      if (v) {
+        const int p = static_cast<int>((static_cast<float>(s) + 0.5f) * rK);  // exact: s < 65536
+        s_list[n + __popc(m & lt_mask)] = static_cast<uint32_t>(s) | (static_cast<uint32_t>(s - p * d.K) << 16);
+      }
+      n += __popc(m);
+    }
+    sparse_w = TMA && !whole_weights && 2 * n <= PK;
+    if (lane == 0) *s_nvalid = sparse_w ? -n - 1 : n;
+    if (TMA && !whole_weights && n > 0) {
+      if (!sparse_w) {  // dense anchor: one copy of the whole block
+        if (lane == 0) {
+          mbar_expect_tx(&bars[1], 4u * wcount);
+          tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
+        }
+      } else {  // sparse anchor: one line per valid sample, packed by valid index
+        if (lane == 0) mbar_expect_tx(&bars[1], 4u * LG * n);
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+          const int s = s_list[i] & 0xffff;
+          tma_bulk_g2s(s_w + i * (LG + MERGE_WPAD), w_g + s * LG, 4u * LG, &bars[1]);
+        }
+      }
+    }
+  }
+  DFA_STAMP(2);
+  __syncthreads();
+  DFA_STAMP(3);
+  int nv = *s_nvalid;
+  sparse_w = nv < 0;
+  nv = sparse_w ? -nv - 1 : nv;
+  if (!TMA) {  // plain staging of the valid samples' weight lines
+    for (int i = tid; i < nv * LG; i += NT) {
+      const int s = s_list[i / LG] & 0xffff, r = i - (i / LG) * LG;
+      s_w[s * LG + r] = __ldg(w_g + s * LG + r);
+    }
+    __syncthreads();
+  }
+  const int wstride = sparse_w ? LG + MERGE_WPAD : LG;
 
-  const int slice = tid >> a.vpr_log2, v = tid & (vpr - 1);
-  const int ch = v * VEC;
-  const int g = ch / (d.C / d.G);
+  const uint32_t rb = 512u * VPL;  // bytes per feature row
   const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
-                            static_cast<size_t>(b) * d.num_feat * rb + static_cast<uint32_t>(ch) * sizeof(T);
-  float acc[VEC];
+                            static_cast<size_t>(b) * d.num_feat * rb + lane * 16;
+  const int gq = (lane * G) / (32 * VPL);  // this lane's group inside each 512-byte segment
+  float acc[VPL][VEC];
 #pragma unroll
-  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-  bool weights_ready = !TMA;
-  const int step = slices * U;
-  const int gq = (d.G + 3) >> 2;  // group quads per row
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[v][c] = 0.f;
 
-  for (int c0 = 0; c0 < ntaps; c0 += a.chunk_taps) {
-    const int nt = min(a.chunk_taps, ntaps - c0);
-    // ---- A: geometry, hash insertion and reference lists — one thread per tap
-    if (tid < nt) {
-      const int t = c0 + tid;
-      const int l = t / nv, i = t - l * nv;  // level-major: same-level neighbours share a chunk
-      const int s = s_list[i];
-      const int kl = (s % d.K) * d.L + l;
+  // A warp's work items: (level, chunk of 8 valid samples) for its levels l = warp, warp + NW, ...
+  const int cpl = (nv + 7) >> 3;  // chunks per level
+  const int my_levels = warp < d.L ? (d.L - warp + NW - 1) / NW : 0;
+  const int max_items = ((d.L + NW - 1) / NW) * cpl;  // warp 0 has the most
+  uint32_t *s_table = reinterpret_cast<uint32_t *>(smem + lay.table) + warp * MERGE_TABLE;
+  uint32_t *my_rowoff = s_rowoff + warp * MERGE_CAP;
+  float *my_coef = s_coef + warp * MERGE_CAP * G;
+  uint32_t *s_mine_off = reinterpret_cast<uint32_t *>(smem + lay.mine_off) + warp * lay.mine_stride;
+  uint16_t *s_mine_slot = reinterpret_cast<uint16_t *>(smem + lay.mine_slot) + warp * lay.mine_stride;
+  bool wready = !TMA;
+  int li = 0, cj = 0;  // this warp's next item: its li-th level, chunk cj
+
+  for (int it0 = 0; it0 < max_items; it0 += 2) {
+    // ---- merge: this warp's next two chunks -------------------------------------------------------
+    int cnt = 0;
+    if (li < my_levels) {
+#pragma unroll
+      for (int x = 0; x < MERGE_TABLE / 128; ++x)
+        reinterpret_cast<uint4 *>(s_table)[x * 32 + lane] =
+            make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      __syncwarp();
+    }
+    for (int x = 0; x < 2 && li < my_levels; ++x) {
+      const int l = warp + li * NW;
+      const int i = (cj << 3) + (lane >> 2), q = lane & 3;
+      if (++cj == cpl) cj = 0, ++li;
+      const bool live = i < nv;
+      const int ii = live ? i : 0;
+      const uint32_t ent = s_list[ii];
+      const int s = ent & 0xffff, k = ent >> 16;
+      const int4 tab = s_tab[k * d.L + l];
+      const float2 xy = *reinterpret_cast<const float2 *>(s_loc + 2 * s);
       TapGeom gm;
-      tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], s_tab[3 * kl], s_tab[3 * kl + 1], s_tab[3 * kl + 2],
-                   gm);
-      const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
-      s_refw[tid] = (s * d.L + l) * d.G;
+      tap_geometry(xy.x, xy.y, tab.x, tab.y, tab.z, gm);
+      const int row = q == 0 ? gm.row[0] : q == 1 ? gm.row[1] : q == 2 ? gm.row[2] : gm.row[3];
+      const float bw = ((q & 2) ? gm.lh : gm.hh) * ((q & 1) ? gm.lw : gm.hw);
+      const bool use = live && row >= 0;
+      const unsigned key = use ? static_cast<unsigned>(row) : (0x80000000u | lane);
+      const unsigned grp = __match_any_sync(0xffffffffu, key);
+      const bool leader = use && (static_cast<int>(__ffs(grp)) - 1 == lane);
+      if (!wready) {
+        mbar_wait(&bars[1], 0);  // weights have landed
+        wready = true;
+      }
+      // coefficients in the permuted order the gather reads them: [gq][v]  (g = v * GPV + gq)
+      float cf[G];
+      {
+        const float4 *wp = reinterpret_cast<const float4 *>(s_w + (sparse_w ? ii : s) * wstride + l * G);
+        float wv[G];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (gm.row[q] < 0) continue;  // outside the map: zero padding, no reference
-        const int key = gm.row[q];
-        int slot = static_cast<int>((static_cast<uint32_t>(key) * 2654435761u) >> (32 - a.hbits));
-        while (true) {
-          const int old = atomicCAS(&s_key[slot], -1, key);
-          if (old == -1) {  // first reference to this row: give it the next dense index
-            const int j = atomicAdd(s_nrows, 1);
-            s_rowoff[j] = static_cast<uint32_t>(key) * rb;
-            s_rowslot[j] = slot;
-            break;
-          }
-          if (old == key) break;
-          slot = (slot + 1) & hmask;
+        for (int x = 0; x < G / 4; ++x) {
+          const float4 t = wp[x];
+          wv[4 * x] = t.x, wv[4 * x + 1] = t.y, wv[4 * x + 2] = t.z, wv[4 * x + 3] = t.w;
         }
-        const int ref = 4 * tid + q;
-        s_refbw[ref] = bw[q];
-        s_refnext[ref] = atomicExch(&s_head[slot], ref);  // push onto the row's reference list
-      }
-    }
-    __syncthreads();
-    if (!weights_ready) {
-      mbar_wait(&bars[1], 0);  // weights have landed
-      weights_ready = true;
-    }
-    // ---- B: coef[row][group] = sum over the row's references of bilinear weight x group weight
-    //         (owner computes: one thread per row and group quad walks the list; no float atomics)
-    const int nrows = *s_nrows;
-    const int nrows_pad = (nrows + step - 1) / step * step;
-    for (int item = tid; item < nrows_pad * gq; item += NT) {
-      const int j = item / gq, g0 = (item - j * gq) * 4;
-      float c4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (j < nrows) {
-        for (int ref = s_head[s_rowslot[j]]; ref >= 0; ref = s_refnext[ref]) {
-          const float bwv = s_refbw[ref];
-          const float *wp = s_w + s_refw[ref >> 2] + g0;
 #pragma unroll
-          for (int x = 0; x < 4; ++x)
-            if (g0 + x < d.G) c4[x] = fmaf(bwv, wp[x], c4[x]);
+        for (int g = 0; g < G; ++g) cf[(g % GPV) * VPL + g / GPV] = use ? bw * wv[g] : 0.f;
+      }
+      // leaders add the coefficients of the other lanes of their group, lowest lane first
+      unsigned rem = leader ? (grp & ~(1u << lane)) : 0u;
+      const int n_it = __reduce_max_sync(0xffffffffu, __popc(rem));
+      for (int it = 0; it < n_it; ++it) {
+        const int src = rem ? (static_cast<int>(__ffs(rem)) - 1) : lane;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float v = __shfl_sync(0xffffffffu, cf[g], src);
+          if (rem) cf[g] += v;
         }
-      } else if (g0 == 0) {
-        s_rowoff[j] = s_rowoff[0];  // padding rows replay row 0 with zero coefficients
+        rem &= rem - 1;
       }
+      // has an earlier chunk of this round listed the row already?
+      const uint32_t h = (static_cast<uint32_t>(row) * 0x9E3779B1u) >> 25;  // MERGE_TABLE = 128
+      const uint32_t e = leader ? s_table[h] : 0xffffffffu;
+      const bool hit = leader && (e >> 6) == static_cast<uint32_t>(row);
+      const bool fresh = leader && !hit;
+      const unsigned fresh_m = __ballot_sync(0xffffffffu, fresh);
+      const int slot = hit ? static_cast<int>(e & 63u) : cnt + __popc(fresh_m & lt_mask);
+      float4 *cp = reinterpret_cast<float4 *>(my_coef + slot * G);
+      if (hit) {
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
-        if (g0 + x < d.G) s_coef[j * d.G + g0 + x] = c4[x];
+        for (int x = 0; x < G / 4; ++x) {
+          float4 t = cp[x];
+          t.x += cf[4 * x], t.y += cf[4 * x + 1], t.z += cf[4 * x + 2], t.w += cf[4 * x + 3];
+          cp[x] = t;
+        }
+      } else if (fresh) {
+        s_table[h] = (static_cast<uint32_t>(row) << 6) | static_cast<uint32_t>(slot);
+        my_rowoff[slot] = static_cast<uint32_t>(row) * rb;
+        if (prefetch == 1)  // start the row's DRAM -> L2 transfer now; the gather then runs at L2 latency
+          tma_prefetch_l2(fb - lane * 16 + static_cast<uint32_t>(row) * rb, rb);
+        else if (prefetch == 2)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fb - lane * 16 + static_cast<uint32_t>(row) * rb));
+#pragma unroll
+        for (int x = 0; x < G / 4; ++x)
+          cp[x] = make_float4(cf[4 * x], cf[4 * x + 1], cf[4 * x + 2], cf[4 * x + 3]);
+      }
+      cnt += __popc(fresh_m);
+      __syncwarp();
     }
+    if (lane == 0) s_cnt[warp] = cnt;
+    DFA_STAMP(4);
     __syncthreads();
-    // ---- C: gather every distinct row once
-    if (slice < slices) {
-      for (int j0 = slice; j0 < nrows_pad; j0 += step) {
-        typename FeatVec<T>::raw_t val[U];
-        float cf[U];
+    DFA_STAMP(5);
+    // ---- this warp's share: slot p of list c goes to warp (p + c) mod NW --------------------------
+    int n_mine = 0;
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          val[u] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + s_rowoff[j0 + u * slices]));
+    for (int c = 0; c < NW; ++c) {
+      const int cn = s_cnt[c];
+      const int first = (warp - c) & (NW - 1);
+      const int mine = cn > first ? (cn - first + NW - 1) / NW : 0;
+      if (lane < mine) {
+        const int slot = c * MERGE_CAP + first + lane * NW;
+        s_mine_off[n_mine + lane] = s_rowoff[slot];
+        s_mine_slot[n_mine + lane] = static_cast<uint16_t>(slot);
+      }
+      n_mine += mine;
+    }
+    if (lane < U) {  // padding up to a multiple of U: no load, zero coefficients
+      s_mine_off[n_mine + lane] = 0xffffffffu;
+      s_mine_slot[n_mine + lane] = 0;
+    }
+    __syncwarp();
+    // ---- gather: every distinct row once ----------------------------------------------------------
+    for (int k0 = 0; k0 < n_mine; k0 += U) {
+      typename FeatVec<T>::raw_t val[U][VPL];
+      uint32_t off[U];
+      int slot[U];
+      if constexpr (U == 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4 *>(s_mine_off + k0);
+        const uint2 s2 = *reinterpret_cast<const uint2 *>(s_mine_slot + k0);
+        off[0] = o4.x, off[1] = o4.y, off[2] = o4.z, off[3] = o4.w;
+        slot[0] = s2.x & 0xffff, slot[1] = s2.x >> 16, slot[2] = s2.y & 0xffff, slot[3] = s2.y >> 16;
+      } else {
+        const uint2 o2 = *reinterpret_cast<const uint2 *>(s_mine_off + k0);
+        const uint32_t s1 = *reinterpret_cast<const uint32_t *>(s_mine_slot + k0);
+        off[0] = o2.x, off[1] = o2.y;
+        slot[0] = s1 & 0xffff, slot[1] = s1 >> 16;
+      }
 #pragma unroll
-        for (int u = 0; u < U; ++u) cf[u] = s_coef[(j0 + u * slices) * d.G + g];
+      for (int u = 0; u < U; ++u) {
+        const bool ok = off[u] != 0xffffffffu;
 #pragma unroll
-        for (int u = 0; u < U; ++u) FeatVec<T>::fma(acc, cf[u], val[u]);
+        for (int v = 0; v < VPL; ++v)
+          val[u][v] = ok ? FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off[u] + 512u * v)))
+                         : FeatVec<T>::zero_raw();
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = off[u] != 0xffffffffu;
+        const float *cp = s_coef + slot[u] * G + gq * VPL;
+        float cv[VPL];
+        if (VPL == 2) {
+          const float2 t = *reinterpret_cast<const float2 *>(cp);
+          cv[0] = ok ? t.x : 0.f, cv[VPL - 1] = ok ? t.y : 0.f;
+        } else {
+          cv[0] = ok ? *cp : 0.f;
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) FeatVec<T>::fma(acc[v], cv[v], val[u][v]);
       }
     }
-    if (c0 + a.chunk_taps < ntaps) {  // more chunks: recycle the table
-      __syncthreads();
-      for (int i = tid; i < hsize; i += NT) s_key[i] = -1, s_head[i] = -1;
-      if (tid == 0) *s_nrows = 0;
-      __syncthreads();
-    }
+    DFA_STAMP(6);
+    __syncthreads();  // the lists are free again (next round, or the partial rows)
   }
-  if (TMA && !weights_ready) mbar_wait(&bars[1], 0);  // never leave with a copy in flight
+  if (TMA && whole_weights && !wready) mbar_wait(&bars[1], 0);  // never exit with a copy in flight
 
-  if (slice < slices) {
-    float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
+  // ---- epilogue: fold the warps' partial rows ---------------------------------------------------
+  {
+    float *part = s_coef + warp * C;
 #pragma unroll
-    for (int c = 0; c < VEC / 4; ++c)
-      r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+    for (int v = 0; v < VPL; ++v) {
+      float4 *o = reinterpret_cast<float4 *>(part + (v * 32 + lane) * VEC);
+#pragma unroll
+      for (int c = 0; c < VEC / 4; ++c)
+        o[c] = make_float4(acc[v][4 * c], acc[v][4 * c + 1], acc[v][4 * c + 2], acc[v][4 * c + 3]);
+    }
   }
   __syncthreads();
-  for (int c = tid; c < d.C; c += NT) {
+  for (int c = tid; c < C; c += NT) {
     float sum = 0.f;
-    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
-    out[static_cast<size_t>(anchor) * d.C + c] = sum;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sum += s_coef[w * C + c];
+    out[static_cast<size_t>(anchor) * C + c] = sum;
   }
+  DFA_STAMP(7);
 }
 
 // Shape-generic forward (any C, G with C % G == 0, any alignment): one CTA per anchor, threads
@@ -1086,6 +1263,166 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Backward of the kernel above: one thread per (b, a) walks the anchor's P key points and K
+// cameras in a fixed order, so the gradients need no atomics and are bitwise reproducible.
+// grad_anchor [bs,A,11] (velocity entries get 0), grad_logits [bs,A,(P-F)*3] (may be NULL).
+__global__ void __launch_bounds__(128)
+    dfa_keypoints_project_bwd_kernel(const float *__restrict__ anchor, const float *__restrict__ fix_scale,
+                                     int num_fix, const float *__restrict__ logits,
+                                     const float *__restrict__ proj, const float *__restrict__ wh,
+                                     const float *__restrict__ grad_loc, float *__restrict__ grad_anchor,
+                                     float *__restrict__ grad_logits, int bs, int A, int P, int K) {
+  const long long ba = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (ba >= static_cast<long long>(bs) * A) return;
+  const int b = static_cast<int>(ba / A);
+  const float *an = anchor + ba * 11;
+  const float size[3] = {expf(an[3]), expf(an[4]), expf(an[5])};
+  const float sn = an[6], cs = an[7];
+  float g_ctr[3] = {0.f, 0.f, 0.f}, g_size[3] = {0.f, 0.f, 0.f}, g_sn = 0.f, g_cs = 0.f;
+  for (int p = 0; p < P; ++p) {
+    float off[3], dsig[3] = {0.f, 0.f, 0.f};
+    if (p < num_fix) {
+      off[0] = fix_scale[3 * p], off[1] = fix_scale[3 * p + 1], off[2] = fix_scale[3 * p + 2];
+    } else {
+      const float *lg = logits + ba * (P - num_fix) * 3 + (p - num_fix) * 3;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float sg = 1.f / (1.f + expf(-lg[i]));
+        off[i] = sg - 0.5f, dsig[i] = sg * (1.f - sg);
+      }
+    }
+    const float ox = off[0] * size[0], oy = off[1] * size[1], oz = off[2] * size[2];
+    const float x = fmaf(cs, ox, -sn * oy) + an[0];
+    const float y = fmaf(sn, ox, cs * oy) + an[1];
+    const float z = oz + an[2];
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float *m = proj + (static_cast<size_t>(b) * K + k) * 16;
+      const float *gl = grad_loc + ((ba * P + p) * K + k) * 2;
+      const float u = fmaf(m[2], z, fmaf(m[1], y, m[0] * x)) + m[3];
+      const float v = fmaf(m[6], z, fmaf(m[5], y, m[4] * x)) + m[7];
+      const float dpt = fmaf(m[10], z, fmaf(m[9], y, m[8] * x)) + m[11];
+      const float den = fmaxf(dpt, 1e-5f);
+      float gpx = gl[0], gpy = gl[1];
+      if (wh) gpx /= wh[(b * K + k) * 2], gpy /= wh[(b * K + k) * 2 + 1];
+      const float gu = gpx / den, gv = gpy / den;
+      // d/d den of (u/den, v/den); the clamp passes the gradient where dpt >= 1e-5 (torch.clamp)
+      const float gd = dpt >= 1e-5f ? -(gu * u + gv * v) / den : 0.f;
+      gx += m[0] * gu + m[4] * gv + m[8] * gd;
+      gy += m[1] * gu + m[5] * gv + m[9] * gd;
+      gz += m[2] * gu + m[6] * gv + m[10] * gd;
+    }
+    g_ctr[0] += gx, g_ctr[1] += gy, g_ctr[2] += gz;
+    const float go[3] = {cs * gx + sn * gy, -sn * gx + cs * gy, gz};  // wrt the rotated-back offset
+    g_cs += ox * gx + oy * gy;
+    g_sn += -oy * gx + ox * gy;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) g_size[i] += off[i] * go[i];
+    if (p >= num_fix && grad_logits) {
+      float *o = grad_logits + ba * (P - num_fix) * 3 + (p - num_fix) * 3;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) o[i] = go[i] * size[i] * dsig[i];
+    }
+  }
+  float *ga = grad_anchor + ba * 11;
+  ga[0] = g_ctr[0], ga[1] = g_ctr[1], ga[2] = g_ctr[2];
+  ga[3] = g_size[0] * size[0], ga[4] = g_size[1] * size[1], ga[5] = g_size[2] * size[2];  // d exp
+  ga[6] = g_sn, ga[7] = g_cs, ga[8] = 0.f, ga[9] = 0.f, ga[10] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// attention weights: softmax over (K, L, P) + attn-drop mask + permute, one pass
+// ------------------------------------------------------------------------------------------
+// logits [bs, A, K, L, P, G] (= weights_fc output, models/blocks.py:175-186) -> weights
+// [bs, A, P, K, L, G] (the op's layout, models/blocks.py:133-144), softmax taken over the N =
+// K*L*P entries of each (b, a, g).  keep [bs, A, K, P] (uint8, may be NULL) is the attn-drop keep
+// mask of models/blocks.py:188-195 and `scale` its 1/(1-p).  One CTA per anchor; the anchor's
+// logits are staged in shared memory once.  Thread t owns group t % G (G divides the block).
+template <int NT>
+__device__ __forceinline__ float group_reduce(float v, float *s_red, int tid, int G, bool is_max) {
+  s_red[tid] = v;
+  __syncthreads();
+  float r = s_red[tid % G];
+  for (int j = (tid % G) + G; j < NT; j += G) r = is_max ? fmaxf(r, s_red[j]) : r + s_red[j];
+  __syncthreads();
+  return r;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    dfa_softmax_weights_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ keep,
+                               float scale, float *__restrict__ w, int K, int L, int P, int G) {
+  extern __shared__ __align__(16) float s_x[];  // N*G logits
+  __shared__ float s_red[NT];
+  const int tid = threadIdx.x, N = K * L * P, n_el = N * G;
+  const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
+  float mx = -INFINITY;
+  for (int e = tid; e < n_el; e += NT) {
+    const float v = __ldg(logits + base + e);
+    s_x[e] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = group_reduce<NT>(mx, s_red, tid, G, true);
+  float sum = 0.f;
+  for (int e = tid; e < n_el; e += NT) {
+    const float v = expf(s_x[e] - mx);
+    s_x[e] = v;
+    sum += v;
+  }
+  sum = group_reduce<NT>(sum, s_red, tid, G, false);
+  const float inv = 1.f / sum;
+  const uint8_t *kp = keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr;
+  for (int e = tid; e < n_el; e += NT) {
+    const int g = e % G, n = e / G;
+    const int p = n % P, kl = n / P, l = kl % L, k = kl / L;
+    float v = s_x[e] * inv;
+    if (kp) v = kp[k * P + p] ? v * scale : 0.f;
+    w[base + ((static_cast<size_t>(p) * K + k) * L + l) * G + g] = v;
+  }
+}
+
+// grad_logits = y * (dy - sum_n dy_n y_n) with y = softmax(logits) recomputed and
+// dy = keep * scale * grad_w (read through the permutation).
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    dfa_softmax_weights_bwd_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ keep,
+                                   float scale, const float *__restrict__ grad_w,
+                                   float *__restrict__ grad_logits, int K, int L, int P, int G) {
+  extern __shared__ __align__(16) float s_x[];  // N*G softmax values, then N*G dy
+  __shared__ float s_red[NT];
+  const int tid = threadIdx.x, N = K * L * P, n_el = N * G;
+  float *s_dy = s_x + n_el;
+  const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
+  float mx = -INFINITY;
+  for (int e = tid; e < n_el; e += NT) {
+    const float v = __ldg(logits + base + e);
+    s_x[e] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = group_reduce<NT>(mx, s_red, tid, G, true);
+  float sum = 0.f;
+  for (int e = tid; e < n_el; e += NT) {
+    const float v = expf(s_x[e] - mx);
+    s_x[e] = v;
+    sum += v;
+  }
+  sum = group_reduce<NT>(sum, s_red, tid, G, false);
+  const float inv = 1.f / sum;
+  const uint8_t *kp = keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr;
+  float dot = 0.f;
+  for (int e = tid; e < n_el; e += NT) {
+    const int g = e % G, n = e / G;
+    const int p = n % P, kl = n / P, l = kl % L, k = kl / L;
+    float dy = __ldg(grad_w + base + ((static_cast<size_t>(p) * K + k) * L + l) * G + g);
+    if (kp) dy = kp[k * P + p] ? dy * scale : 0.f;
+    const float y = s_x[e] * inv;
+    s_x[e] = y, s_dy[e] = dy;
+    dot = fmaf(dy, y, dot);
+  }
+  dot = group_reduce<NT>(dot, s_red, tid, G, false);
+  for (int e = tid; e < n_el; e += NT) grad_logits[base + e] = s_x[e] * (s_dy[e] - dot);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1200,52 +1537,87 @@ inline int env_int(const char *name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <typename T, int U, bool TMA, int NT, int MINB>
-int launch_fwd_dedup(const void *feat, const int *shape, const int *start, const float *loc,
-                     const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
-  auto kern = dfa_fwd_dedup_kernel<T, U, TMA, NT, MINB>;
-  const int slices = NT / vpr;
-  DedupArgs a;
-  a.vpr_log2 = 0;
-  while ((1 << a.vpr_log2) < vpr) ++a.vpr_log2;
-  // taps per chunk: one thread per tap, and coef[4*chunk][G] kept near 8 KB
-  a.chunk_taps = 64;
-  while (a.chunk_taps > 8 && 4 * a.chunk_taps * d.G * 4 > 8192) a.chunk_taps >>= 1;
-  a.lay = smem_layout3(d.P, d.K, d.L, d.G, d.C, slices, a.chunk_taps, U);
-  a.hbits = static_cast<int>(a.lay.hbits);
-  if (int rc = set_smem(kern, a.lay.total)) return rc;
-  kern<<<d.bs * d.A, NT, a.lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w, out,
-                                            d, a);
+template <typename T, int VPL, int NW, int U, bool TMA, int MINB>
+int launch_fwd_merge(const void *feat, const int *shape, const int *start, const float *loc,
+                     const float *w, float *out, const Dims &d, cudaStream_t st) {
+  auto kern = dfa_fwd_merge_kernel<T, VPL, 8, NW, U, TMA, MINB>;
+  const MergeLayout lay = merge_layout(d.P, d.K, d.L, d.G, NW, U);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  // A grid that fits the machine in about one wave is bound by latency, not bandwidth: fetch the
+  // whole weights block at once instead of waiting for the sample mask first.
+  const long long grid = static_cast<long long>(d.bs) * d.A;
+  const int whole = env_int("DFA_FWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0);
+  const int prefetch = env_int("DFA_FWD_PREFETCH", 0);
+  kern<<<d.bs * d.A, NW * 32, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
+                                              out, d, lay, whole, prefetch);
   return static_cast<int>(cudaGetLastError());
+}
+
+// The merging kernel applies when a feature row is 512 or 1024 bytes (a lane owns one or two
+// 16-byte vectors of it) and there are 8 channel groups — SimPB's C=256 / G=8 in fp32 and bf16.
+// Returns vectors per lane, 0 when the shape does not fit.
+template <typename T>
+int merge_vpl(const Dims &d, const void *feat) {
+  const long long rb = static_cast<long long>(d.C) * static_cast<long long>(sizeof(T));
+  if (d.G != 8 || !aligned(feat, 16)) return 0;
+  if (rb != 512 && rb != 1024) return 0;
+  if (d.K > 64 || static_cast<long long>(d.P) * d.K >= 65536) return 0;  // packed sample list
+  if (static_cast<long long>(d.num_feat) * rb >= (1ll << 32)) return 0;
+  const MergeLayout lay = merge_layout(d.P, d.K, d.L, d.G, 8, 8);
+  if (lay.total > 200u * 1024u) return 0;
+  return static_cast<int>(rb / 512);
+}
+
+// TMA staging needs 16-byte sized and aligned blocks, and byte counts an mbarrier can track.
+inline bool warp_tma_ok(const Dims &d, const float *loc, const float *w) {
+  const long long line = 4ll * d.L * d.G, wbytes = line * d.P * d.K, lbytes = 8ll * d.P * d.K;
+  return line % 16 == 0 && lbytes % 16 == 0 && wbytes < (1ll << 20) && aligned(loc, 16) &&
+         aligned(w, 16);
 }
 
 template <typename T>
 int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
                   const float *w, float *out, const Dims &d, cudaStream_t st) {
-  // DFA_FWD_VARIANT (tuning knob): 0 = one-warp-per-group kernel, 1..4 = row-sliced kernel with
-  // (threads, taps in flight) = (256,1) (256,2) (512,1) (512,2)
-  const int variant = env_int("DFA_FWD_VARIANT", 5);
-  if (variant >= 5) {  // 5, 6: row-deduplicated kernel with 4 / 8 rows in flight per thread
-    const int vpr = rows_vpr<T>(d, feat, 256);
-    if (vpr) {
-      const bool tma = tma_ok(d, loc, w);
-      if (variant == 5)
-        return tma ? launch_fwd_dedup<T, 4, true, 256, 6>(feat, shape, start, loc, w, out, d, vpr, st)
-                   : launch_fwd_dedup<T, 4, false, 256, 6>(feat, shape, start, loc, w, out, d, vpr, st);
-      return tma ? launch_fwd_dedup<T, 8, true, 256, 4>(feat, shape, start, loc, w, out, d, vpr, st)
-                 : launch_fwd_dedup<T, 8, false, 256, 4>(feat, shape, start, loc, w, out, d, vpr, st);
+  // DFA_FWD_VARIANT (tuning knob): 1..4 = row-sliced kernel with (threads, taps in flight) =
+  // (256,1) (256,2) (512,1) (512,2) — 1 is the default, the fastest measured on B200 at SimPB's
+  // shapes; 10.. = row-merging kernel (fewer DRAM bytes and L1 wavefronts, longer dependent chain
+  // per warp: within 5-25 % of the default); 0 = one-warp-per-group kernel.
+  // A variant whose shape constraints are not met falls through to the next family.
+  const int variant = env_int("DFA_FWD_VARIANT", 1);
+  if (variant >= 10) {  // merging kernel: (warps, rows in flight, CTAs per SM) per variant
+    const int vpl = merge_vpl<T>(d, feat);
+    if (vpl) {
+      const bool tma = warp_tma_ok(d, loc, w);
+#define WARPK(VPL, NW, U, MINB)                                                                  \
+  (tma ? launch_fwd_merge<T, VPL, NW, U, true, MINB>(feat, shape, start, loc, w, out, d, st)       \
+       : launch_fwd_merge<T, VPL, NW, U, false, MINB>(feat, shape, start, loc, w, out, d, st))
+#define WARPV(NW, U, MINB) (vpl == 2 ? WARPK(2, NW, U, MINB) : WARPK(1, NW, U, MINB))
+      switch (variant) {
+        case 11: return WARPV(4, 4, 8);
+        case 12: return WARPV(4, 4, 9);
+        case 13: return WARPV(4, 2, 12);
+        case 14: return WARPV(8, 4, 5);
+        case 15: return WARPV(8, 4, 4);
+        case 16: return WARPV(8, 2, 6);
+        case 17: return WARPV(2, 4, 18);
+        default: return WARPV(4, 4, 10);
+      }
+#undef WARPV
+#undef WARPK
     }
-  } else if (variant >= 1) {
-    const int nt = variant >= 3 ? 512 : 256;
+  }
+  const int rvariant = variant >= 10 ? 1 : variant;
+  if (rvariant >= 1) {
+    const int nt = rvariant >= 3 ? 512 : 256;
     const int vpr = rows_vpr<T>(d, feat, nt);
     if (vpr) {
       const bool tma = tma_ok(d, loc, w);
-      const bool pf = env_int("DFA_FWD_PREFETCH", 1) != 0;
+      const bool pf = env_int("DFA_FWD_PREFETCH", 0) != 0;
 #define ROWS(U, NT, MINB)                                                                              \
   (tma ? (pf ? launch_fwd_rows<T, U, true, NT, MINB, true>(feat, shape, start, loc, w, out, d, vpr, st)  \
              : launch_fwd_rows<T, U, true, NT, MINB, false>(feat, shape, start, loc, w, out, d, vpr, st)) \
        : launch_fwd_rows<T, U, false, NT, MINB, false>(feat, shape, start, loc, w, out, d, vpr, st))
-      switch (variant) {
+      switch (rvariant) {
         case 1: return ROWS(1, 256, 6);
         case 2: return ROWS(2, 256, 4);
         case 3: return ROWS(1, 512, 3);
@@ -1308,6 +1680,12 @@ int backward_typed(const void *feat, const int *shape, const int *start, const f
 extern "C" {
 
 int dfa_version(void) { return DFA_B200_VERSION; }
+
+#ifdef DFA_PHASE_TIMING
+int dfa_debug_set_phase_buffer(long long *buf) {
+  return static_cast<int>(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)));
+}
+#endif
 
 const char *dfa_error_string(int code) {
   switch (code) {
@@ -1439,6 +1817,66 @@ int dfa_keypoints_project(const float *anchor, const float *fix_scale, int num_f
                                  static_cast<cudaStream_t>(stream)>>>(
       anchor, fix_scale, num_fix, learnable_logits, projection_mat, image_wh, key_points,
       sampling_location, bs, num_anchors, num_pts, num_cams);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int dfa_keypoints_project_backward(const float *anchor, const float *fix_scale, int num_fix,
+                                   const float *learnable_logits, const float *projection_mat,
+                                   const float *image_wh, const float *grad_sampling_location,
+                                   float *grad_anchor, float *grad_learnable_logits, int bs,
+                                   int num_anchors, int num_pts, int num_cams, void *stream) {
+  if (!anchor || !fix_scale || !projection_mat || !grad_sampling_location || !grad_anchor)
+    return DFA_ERR_NULL_POINTER;
+  if (bs <= 0 || num_anchors <= 0 || num_pts <= 0 || num_cams <= 0 || num_fix < 0 || num_fix > num_pts)
+    return DFA_ERR_BAD_DIMS;
+  if (num_fix < num_pts && !learnable_logits) return DFA_ERR_NULL_POINTER;
+  const long long n = static_cast<long long>(bs) * num_anchors;
+  if (n * num_pts >= (1ll << 31)) return DFA_ERR_BAD_DIMS;
+  dfa_keypoints_project_bwd_kernel<<<static_cast<int>((n + 127) / 128), 128, 0,
+                                     static_cast<cudaStream_t>(stream)>>>(
+      anchor, fix_scale, num_fix, learnable_logits, projection_mat, image_wh, grad_sampling_location,
+      grad_anchor, grad_learnable_logits, bs, num_anchors, num_pts, num_cams);
+  return static_cast<int>(cudaGetLastError());
+}
+
+namespace {
+constexpr int SOFTMAX_NT = 256;
+int softmax_check(long long n_anchors, int K, int L, int P, int G, long long smem_floats, uint32_t *smem) {
+  if (n_anchors <= 0 || K <= 0 || L <= 0 || P <= 0 || G <= 0) return DFA_ERR_BAD_DIMS;
+  if (n_anchors >= (1ll << 31) || SOFTMAX_NT % G != 0) return DFA_ERR_UNSUPPORTED;
+  const long long bytes = 4ll * K * L * P * G * smem_floats;
+  if (bytes > 200ll * 1024) return DFA_ERR_UNSUPPORTED;
+  *smem = static_cast<uint32_t>(bytes);
+  return 0;
+}
+}  // namespace
+
+int dfa_softmax_weights(const float *logits, const uint8_t *keep_mask, float scale, float *weights,
+                        int bs, int num_anchors, int num_cams, int num_scale, int num_pts,
+                        int num_groups, void *stream) {
+  if (!logits || !weights) return DFA_ERR_NULL_POINTER;
+  uint32_t smem = 0;
+  const long long n = static_cast<long long>(bs) * num_anchors;
+  if (int rc = softmax_check(n, num_cams, num_scale, num_pts, num_groups, 1, &smem)) return rc;
+  auto kern = dfa_softmax_weights_kernel<SOFTMAX_NT>;
+  if (int rc = set_smem(kern, smem)) return rc;
+  kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
+      logits, keep_mask, scale, weights, num_cams, num_scale, num_pts, num_groups);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int dfa_softmax_weights_backward(const float *logits, const uint8_t *keep_mask, float scale,
+                                 const float *grad_weights, float *grad_logits, int bs,
+                                 int num_anchors, int num_cams, int num_scale, int num_pts,
+                                 int num_groups, void *stream) {
+  if (!logits || !grad_weights || !grad_logits) return DFA_ERR_NULL_POINTER;
+  uint32_t smem = 0;
+  const long long n = static_cast<long long>(bs) * num_anchors;
+  if (int rc = softmax_check(n, num_cams, num_scale, num_pts, num_groups, 2, &smem)) return rc;
+  auto kern = dfa_softmax_weights_bwd_kernel<SOFTMAX_NT>;
+  if (int rc = set_smem(kern, smem)) return rc;
+  kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
+      logits, keep_mask, scale, grad_weights, grad_logits, num_cams, num_scale, num_pts, num_groups);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -1,0 +1,71 @@
+"""Where does a CTA of the merging forward kernel spend its life?  Builds a tool-only copy of the
+library with -DDFA_PHASE_TIMING (clock64 stamps at phase boundaries) and prints per-phase cycle
+statistics.   python tools/phase_timing.py [--batch B] [--variant V]
+"""
+import argparse
+import ctypes
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from simpb_b200 import build, synthetic  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--variant", type=int, default=10)
+ap.add_argument("--nw", type=int, default=4)
+ap.add_argument("--inputs", default="rig")
+a = ap.parse_args()
+os.environ["DFA_FWD_VARIANT"] = str(a.variant)
+lib_path = os.path.join(ROOT, "gpurun_out", "libdfa_b200_prof.so")
+os.makedirs(os.path.dirname(lib_path), exist_ok=True)
+subprocess.check_call(["nvcc"] + build.NVCC_FLAGS + ["-DDFA_PHASE_TIMING", "-I", os.path.join(ROOT, "include"),
+                                                    "-o", lib_path, build.KERNEL_SRC])
+lib = ctypes.CDLL(lib_path)
+
+
+class Dims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("bs", "K", "nf", "C", "L", "A", "P", "G")]
+
+
+maker = synthetic.rig_op_inputs if a.inputs == "rig" else synthetic.op_inputs_uniform
+sets = []
+for s in range(3):
+    d = maker(bs=a.batch, seed=s)
+    sets.append(dict(feat=d["mc_ms_feat"].cuda(), shape=d["spatial_shape"].int().cuda(),
+                     start=d["scale_start_index"].int().cuda(), loc=d["sampling_location"].cuda(),
+                     w=d["weights"].cuda(), nf=d["num_feat"]))
+n_anchor = a.batch * 900
+buf = torch.zeros(n_anchor, a.nw, 8, dtype=torch.int64, device="cuda")
+out = torch.empty(a.batch, 900, 256, device="cuda")
+vp = ctypes.c_void_p
+lib.dfa_debug_set_phase_buffer.argtypes = [vp]
+lib.dfa_forward.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp, ctypes.POINTER(Dims), vp]
+assert lib.dfa_debug_set_phase_buffer(buf.data_ptr()) == 0
+st = torch.cuda.current_stream().cuda_stream
+for i in range(3):   # the last launch (cold inputs: 3 sets rotate) is the one analysed
+    g = sets[i]
+    dm = Dims(a.batch, 6, g["nf"], 256, 4, 900, 13, 8)
+    rc = lib.dfa_forward(g["feat"].data_ptr(), 0, g["shape"].data_ptr(), g["start"].data_ptr(),
+                         g["loc"].data_ptr(), g["w"].data_ptr(), out.data_ptr(), ctypes.byref(dm), st)
+    assert rc == 0, rc
+torch.cuda.synchronize()
+t = buf.cpu().double()
+names = ["0 start", "1 loc landed / tables", "2 compaction+weights issued", "3 barrier A", "4 merge done",
+         "5 barrier B", "6 gather done", "7 end"]
+t0 = t[:, :, 0].min(dim=1, keepdim=True).values          # CTA start
+print("variant", a.variant, "batch", a.batch, "anchors", n_anchor)
+print("phase stamps relative to CTA start, cycles: median / p90 / max over (anchor, warp)")
+for i in range(1, 8):
+    x = (t[:, :, i] - t0).flatten()
+    x = x[t[:, :, i].flatten() > 0]
+    if x.numel():
+        print("  %-30s %8.0f %8.0f %8.0f" % (names[i], x.median(), x.quantile(0.9), x.max()))
+life = (t[:, :, 7].max(dim=1).values - t0[:, 0])
+print("CTA lifetime: median %.0f p90 %.0f max %.0f cycles" % (life.median(), life.quantile(0.9), life.max()))
+span = t[:, :, 7].max() - t[:, :, 0][t[:, :, 0] > 0].min()
+print("(clock64 is per SM; first start to last end across SMs is only indicative: %.0f cycles)" % span)

@@ -1,0 +1,30 @@
+"""Compact per-kernel register / spill / shared-memory report from `nvcc -Xptxas -v`.
+    python tools/ptxas_report.py [substring]
+"""
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from simpb_b200 import build  # noqa: E402
+
+cmd = ["nvcc"] + build.NVCC_FLAGS + ["-Xptxas=-v", "-I", os.path.join(ROOT, "include"), "-o", build.LIB,
+                                     build.KERNEL_SRC]
+err = subprocess.run(cmd, capture_output=True, text=True).stderr
+filt = sys.argv[1] if len(sys.argv) > 1 else ""
+name = None
+for line in err.splitlines():
+    m = re.search(r"Compiling entry function '(\S+)'", line)
+    if m:
+        name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        name = name.replace("(anonymous namespace)::", "").replace("void ", "")
+        name = re.sub(r"\(.*", "", name)
+        spill = ""
+    m = re.search(r"(\d+) bytes spill stores, (\d+) bytes spill loads", line)
+    if m and (m.group(1) != "0" or m.group(2) != "0"):
+        spill = " SPILL st=%s ld=%s" % m.groups()
+    m = re.search(r"Used (\d+) registers", line)
+    if m and name and filt in name:
+        print("%-70s regs=%s%s" % (name, m.group(1), spill))

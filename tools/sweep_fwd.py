@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from simpb_b200 import cabi, synthetic  # noqa: E402
 import bench  # noqa: E402
 
-variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "0,1,2,3,4").split(",")]
+variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,10,11,15").split(",")]
 cases = [("rig", 1, "f32"), ("uniform", 1, "f32"), ("rig", 8, "f32"), ("rig", 1, "bf16"), ("rig", 8, "bf16")]
 for inputs, batch, dt in cases:
     maker = synthetic.rig_op_inputs if inputs == "rig" else synthetic.op_inputs_uniform
@@ -17,7 +17,7 @@ for inputs, batch, dt in cases:
     sets = [bench.to_device(maker(bs=batch, seed=s), dtype) for s in range(n_sets)]
     outs = [torch.empty(batch, 900, 256, device="cuda") for _ in sets]
     ref = None
-    for v, pf in [(v, pf) for v in variants for pf in ((0, 1) if v > 0 else (0,))]:
+    for v, pf in [(v, pf) for v in variants for pf in ((0, 1, 2) if v >= 10 else (0,))]:
         os.environ["DFA_FWD_VARIANT"] = str(v)
         os.environ["DFA_FWD_PREFETCH"] = str(pf)
         fns = [(lambda g=g, o=o: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o))
