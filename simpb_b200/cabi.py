@@ -17,8 +17,9 @@ BWD_ACCUMULATE, BWD_OVERWRITE_SMALL, BWD_ZERO_GRAD_FEAT = 0, 1, 2
 
 # every symbol include/dfa_b200.h declares (tests check the library exports each of them)
 SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_forward", "dfa_backward", "dfa_debug_indices",
-           "dfa_flatten_maps", "dfa_keypoints_project", "dfa_forward_host_workspace_bytes",
-           "dfa_forward_host")
+           "dfa_flatten_maps", "dfa_keypoints_project", "dfa_keypoints_project_backward",
+           "dfa_softmax_weights", "dfa_softmax_weights_backward",
+           "dfa_forward_host_workspace_bytes", "dfa_forward_host")
 
 
 class DfaError(RuntimeError):
@@ -45,11 +46,17 @@ def _load():
     lib.dfa_debug_indices.argtypes = [vp, vp, vp, vp, vp, dp, vp]
     lib.dfa_flatten_maps.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp]
     lib.dfa_keypoints_project.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.dfa_keypoints_project_backward.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32,
+                                                   i32, vp]
+    f32 = ctypes.c_float
+    lib.dfa_softmax_weights.argtypes = [vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.dfa_softmax_weights_backward.argtypes = [vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.dfa_forward_host_workspace_bytes.restype = i64
     lib.dfa_forward_host_workspace_bytes.argtypes = [i32, dp]
     lib.dfa_forward_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp, i64, vp]
     for name in ("dfa_forward", "dfa_backward", "dfa_debug_indices", "dfa_flatten_maps",
-                 "dfa_keypoints_project", "dfa_forward_host"):
+                 "dfa_keypoints_project", "dfa_keypoints_project_backward", "dfa_softmax_weights",
+                 "dfa_softmax_weights_backward", "dfa_forward_host"):
         getattr(lib, name).restype = i32
     return lib
 
@@ -213,6 +220,78 @@ def keypoints_project(anchor, fix_scale, learnable_logits, projection_mat, image
             kp.data_ptr() if kp is not None else None, loc.data_ptr(), bs, A, P, K,
             stream_ptr(anchor.device)), "dfa_keypoints_project")
     return (loc, kp) if want_key_points else loc
+
+
+def _kp_dims(anchor, fix_scale, learnable_logits, projection_mat):
+    bs, A = anchor.shape[:2]
+    if anchor.dim() != 3 or anchor.shape[2] != 11:
+        raise DfaError("anchor must be [bs, A, 11]")
+    F_ = fix_scale.shape[0]
+    n_learn = 0 if learnable_logits is None else learnable_logits.numel() // (bs * A * 3)
+    return bs, A, F_, F_ + n_learn, projection_mat.shape[1]
+
+
+def keypoints_project_backward(anchor, fix_scale, learnable_logits, projection_mat, image_wh, grad_loc):
+    """Gradients of keypoints_project wrt the anchor and the learnable-offset logits."""
+    _need(anchor, "anchor", torch.float32); _need(fix_scale, "fix_scale", torch.float32)
+    _need(projection_mat, "projection_mat", torch.float32)
+    _need(grad_loc, "grad_sampling_location", torch.float32)
+    if learnable_logits is not None:
+        _need(learnable_logits, "learnable_logits", torch.float32)
+    if image_wh is not None:
+        _need(image_wh, "image_wh", torch.float32)
+    bs, A, F_, P, K = _kp_dims(anchor, fix_scale, learnable_logits, projection_mat)
+    if tuple(grad_loc.shape) != (bs, A, P, K, 2):
+        raise DfaError("grad_sampling_location must be [bs, A, P, K, 2]")
+    g_anchor = torch.empty_like(anchor)
+    g_logits = torch.empty_like(learnable_logits) if learnable_logits is not None else None
+    with torch.cuda.device(anchor.device):
+        check(lib.dfa_keypoints_project_backward(
+            anchor.data_ptr(), fix_scale.data_ptr(), F_,
+            learnable_logits.data_ptr() if learnable_logits is not None else None,
+            projection_mat.data_ptr(), image_wh.data_ptr() if image_wh is not None else None,
+            grad_loc.data_ptr(), g_anchor.data_ptr(),
+            g_logits.data_ptr() if g_logits is not None else None, bs, A, P, K,
+            stream_ptr(anchor.device)), "dfa_keypoints_project_backward")
+    return g_anchor, g_logits
+
+
+def _softmax_args(logits, dims, keep):
+    _need(logits, "logits", torch.float32)
+    bs, A, K, L, P, G = dims
+    if logits.numel() != bs * A * K * L * P * G:
+        raise DfaError("logits must hold bs*A*K*L*P*G elements")
+    if keep is not None:
+        _need(keep, "keep_mask", torch.uint8)
+        if keep.numel() != bs * A * K * P:
+            raise DfaError("keep_mask must be uint8 [bs, A, K, P]")
+
+
+def softmax_weights(logits, dims, keep=None, scale=1.0):
+    """logits in (bs, A, K, L, P, G) memory order → weights [bs, A, P, K, L, G]; dims = that tuple."""
+    _softmax_args(logits, dims, keep)
+    bs, A, K, L, P, G = dims
+    w = torch.empty(bs, A, P, K, L, G, device=logits.device, dtype=torch.float32)
+    with torch.cuda.device(logits.device):
+        check(lib.dfa_softmax_weights(logits.data_ptr(), keep.data_ptr() if keep is not None else None,
+                                      float(scale), w.data_ptr(), bs, A, K, L, P, G,
+                                      stream_ptr(logits.device)), "dfa_softmax_weights")
+    return w
+
+
+def softmax_weights_backward(logits, dims, keep, scale, grad_w):
+    _softmax_args(logits, dims, keep)
+    _need(grad_w, "grad_weights", torch.float32)
+    bs, A, K, L, P, G = dims
+    if grad_w.numel() != logits.numel():
+        raise DfaError("grad_weights must be [bs, A, P, K, L, G]")
+    g = torch.empty_like(logits)
+    with torch.cuda.device(logits.device):
+        check(lib.dfa_softmax_weights_backward(
+            logits.data_ptr(), keep.data_ptr() if keep is not None else None, float(scale),
+            grad_w.data_ptr(), g.data_ptr(), bs, A, K, L, P, G, stream_ptr(logits.device)),
+            "dfa_softmax_weights_backward")
+    return g
 
 
 class HostForward:

@@ -18,6 +18,30 @@ def deformable_aggregation_function(feature_maps, spatial_shape, scale_start_ind
                                                sampling_location, weights)
 
 
+class _FlattenMaps(torch.autograd.Function):
+    """col_feats = flatten(maps) with the transposing kernel; the backward hands every level its
+    slice of grad_col_feats back in NCHW (the reference gets this from autograd through its
+    reshape / cat / permute chain)."""
+
+    @staticmethod
+    def forward(ctx, dtype, *maps):
+        ctx.shapes = [tuple(m.shape) for m in maps]
+        return cabi.flatten_maps(list(maps), out_dtype=dtype)
+
+    @staticmethod
+    def backward(ctx, grad_col):
+        bs, K, C = ctx.shapes[0][:3]
+        per_cam = sum(s[3] * s[4] for s in ctx.shapes)
+        g = grad_col.reshape(bs, K, per_cam, C)
+        out, o = [], 0
+        for s in ctx.shapes:
+            h, w = s[3], s[4]
+            out.append(g[:, :, o:o + h * w].reshape(bs, K, h, w, C).permute(0, 1, 4, 2, 3)
+                       .contiguous().float())
+            o += h * w
+        return (None,) + tuple(out)
+
+
 def _tables(sizes, num_cams, device):
     shape = torch.tensor([list(sizes)] * num_cams, dtype=torch.int64, device=device)
     counts = (shape[..., 0] * shape[..., 1]).flatten()
@@ -67,6 +91,6 @@ def feature_maps_format(feature_maps, inverse=False, dtype=None):
 
     maps = [m.contiguous().float() for m in feature_maps]
     K = maps[0].shape[1]
-    col = cabi.flatten_maps(maps, out_dtype=dtype or torch.float32)
+    col = _FlattenMaps.apply(dtype or torch.float32, *maps)
     shape, start = _tables([tuple(m.shape[-2:]) for m in maps], K, col.device)
     return [col, shape, start]
