@@ -138,7 +138,7 @@ def algorithmic_bytes(d, esz, distinct_rows):
     return fixed + distinct_rows * C * esz, fixed + bs * d["num_feat"] * C * esz
 
 
-def time_graph(fn_list, steps, warmup, use_graph, sync_all):
+def time_graph(fn_list, steps, warmup, use_graph, sync_all, finalize=None):
     """Times `steps` launches cycling through fn_list (one callable per rotating input set).
     Returns total milliseconds measured by CUDA events on the current stream."""
     n = len(fn_list)
@@ -167,6 +167,8 @@ def time_graph(fn_list, steps, warmup, use_graph, sync_all):
         else:
             for i in range(steps):
                 fn_list[i % n]()
+        if finalize is not None:
+            finalize()          # e.g. join the communication stream: its work belongs to the steps
         e1.record(stream)
         stream.synchronize()
         sync_all()
@@ -267,18 +269,27 @@ def run_own_arm(args):
     sets = [to_device(d, dtype) for d in host]
     outs = [torch.empty(args.batch, args.anchors, 256, device="cuda") for _ in sets]
     launches_per_step = 1
+    finalize = None
 
     if args.workload == "fwd":
         fns = [(lambda g=g, o=o: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o))
                for g, o in zip(sets, outs)]
     else:
-        # training step of the op: forward, backward (grad_feat memset inside), then the
-        # data-parallel all-reduce of a DFA-parameter-sized gradient bucket (247,495 fp32 x 3 layers)
+        # training step of the op: forward, backward (grad_feat memset inside), then the data-parallel
+        # all-reduce (mean) of a gradient bucket the size of the three DFA layers' parameters
+        # (3 x 247,495 fp32), enqueued on a side stream so it overlaps the next step's kernels
+        from simpb_b200 import parallel
         gfs = [torch.empty_like(g["feat"], dtype=torch.float32) for g in sets[:2]]
         gls = [torch.empty_like(g["loc"]) for g in sets]
         gws = [torch.empty_like(g["w"]) for g in sets]
-        bucket = torch.zeros(3 * 247495, device="cuda")
-        launches_per_step = 2
+        params = [torch.nn.Parameter(torch.zeros(247495, device="cuda")) for _ in range(3)]
+        for p in params:
+            p.grad = torch.ones_like(p)
+        bucket = None
+        if dist is not None:
+            bucket = parallel.GradBucket(params, comm_stream=torch.cuda.Stream())
+            finalize = bucket.wait
+        launches_per_step = 3          # forward, grad_feat memset, backward (+ NCCL's own kernels)
 
         def mk(i, g, o):
             def f():
@@ -286,14 +297,15 @@ def run_own_arm(args):
                 cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
                               gfs[i % 2], gls[i], gws[i],
                               flags=cabi.BWD_OVERWRITE_SMALL | cabi.BWD_ZERO_GRAD_FEAT)
-                if dist is not None:
-                    dist.all_reduce(bucket)
+                if bucket is not None:
+                    bucket.wait()                 # previous step's all-reduce must have landed
+                    bucket.all_reduce_mean()
             return f
         fns = [mk(i, g, o) for i, (g, o) in enumerate(zip(sets, outs))]
 
     use_graph = not args.no_graph and not (args.workload == "train" and dist is not None)
     with ClockSampler(local) as clk:
-        total_ms = time_graph(fns, args.steps, args.warmup, use_graph, sync_all)
+        total_ms = time_graph(fns, args.steps, args.warmup, use_graph, sync_all, finalize)
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
