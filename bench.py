@@ -291,12 +291,22 @@ def run_own_arm(args):
             finalize = bucket.wait
         launches_per_step = 3          # forward, grad_feat memset, backward (+ NCCL's own kernels)
 
+        fill_stream = torch.cuda.Stream()
+
         def mk(i, g, o):
             def f():
+                # what DeformableAggregationFunction does: the zero-fill of the scatter target runs
+                # on a side stream under the forward, the backward waits for it
+                cur = torch.cuda.current_stream()
+                fill_stream.wait_stream(cur)
+                with torch.cuda.stream(fill_stream):
+                    gfs[i % 2].zero_()
+                    filled = torch.cuda.Event()
+                    filled.record(fill_stream)
                 cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o)
+                cur.wait_event(filled)
                 cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
-                              gfs[i % 2], gls[i], gws[i],
-                              flags=cabi.BWD_OVERWRITE_SMALL | cabi.BWD_ZERO_GRAD_FEAT)
+                              gfs[i % 2], gls[i], gws[i], flags=cabi.BWD_OVERWRITE_SMALL)
                 if bucket is not None:
                     bucket.wait()                 # previous step's all-reduce must have landed
                     bucket.all_reduce_mean()

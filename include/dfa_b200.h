@@ -81,7 +81,8 @@ int dfa_forward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_s
                 const float *weights, float *output, const dfa_dims *dims, void *stream);
 
 /* Gradients wrt features, sampling locations and weights.  grad_mc_ms_feat is float32
- * [bs,num_feat,C] whatever feat_dtype is, and is always accumulated into (scatter). */
+ * [bs,num_feat,C] whatever feat_dtype is, and is always accumulated into (scatter); it may be NULL
+ * (frozen backbone): the scatter and its zero-fill are then skipped altogether. */
 int dfa_backward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_shape,
                  const int32_t *scale_start_index, const float *sampling_location,
                  const float *weights, const float *grad_output, float *grad_mc_ms_feat,

@@ -127,9 +127,10 @@ def forward(feat, shape, start, loc, w, out=None):
 
 
 def backward(feat, shape, start, loc, w, grad_out, grad_feat=None, grad_loc=None, grad_w=None,
-             flags=None):
+             flags=None, need_feat=True):
     """With no buffers given: allocates them, lets the kernel write the two small gradients in full
-    and zero-fills grad_feat on the stream (one memset instead of the reference's three)."""
+    and zero-fills grad_feat on the stream (one memset instead of the reference's three).
+    need_feat=False skips the feature gradient (scatter and zero-fill) and returns None for it."""
     _need(feat, "mc_ms_feat"); _need(shape, "spatial_shape", torch.int32)
     _need(start, "scale_start_index", torch.int32)
     _need(loc, "sampling_location", torch.float32); _need(w, "weights", torch.float32)
@@ -138,25 +139,27 @@ def backward(feat, shape, start, loc, w, grad_out, grad_feat=None, grad_loc=None
     if tuple(grad_out.shape) != (d.batch_size, d.num_anchors, d.num_embeds):
         raise DfaError("grad_output must be [bs, anchors, embeds]")
     if flags is None:
-        flags = BWD_ACCUMULATE if (grad_feat is not None and grad_loc is not None
-                                   and grad_w is not None) else None
-    if flags is None:
-        flags = BWD_OVERWRITE_SMALL
-        if grad_feat is None:
+        all_given = (grad_feat is not None or not need_feat) and grad_loc is not None and grad_w is not None
+        flags = BWD_ACCUMULATE if all_given else BWD_OVERWRITE_SMALL
+        if grad_feat is None and need_feat:
             grad_feat = torch.empty(feat.shape, device=feat.device, dtype=torch.float32)
             flags |= BWD_ZERO_GRAD_FEAT
-        grad_loc = torch.empty_like(loc) if grad_loc is None else grad_loc
-        grad_w = torch.empty_like(w) if grad_w is None else grad_w
+    grad_loc = torch.empty_like(loc) if grad_loc is None else grad_loc
+    grad_w = torch.empty_like(w) if grad_w is None else grad_w
+    if not need_feat:
+        grad_feat = None
     for t, n in ((grad_feat, "grad_mc_ms_feat"), (grad_loc, "grad_sampling_location"),
                  (grad_w, "grad_weights")):
-        _need(t, n, torch.float32)
-    if grad_feat.numel() != feat.numel() or grad_loc.numel() != loc.numel() \
+        if t is not None:
+            _need(t, n, torch.float32)
+    if (grad_feat is not None and grad_feat.numel() != feat.numel()) or grad_loc.numel() != loc.numel() \
             or grad_w.numel() != w.numel():
         raise DfaError("gradient buffer sizes do not match their inputs")
     with torch.cuda.device(feat.device):
         check(lib.dfa_backward(feat.data_ptr(), feat_dtype(feat), shape.data_ptr(), start.data_ptr(),
                                loc.data_ptr(), w.data_ptr(), grad_out.data_ptr(),
-                               grad_feat.data_ptr(), grad_loc.data_ptr(), grad_w.data_ptr(),
+                               grad_feat.data_ptr() if grad_feat is not None else None,
+                               grad_loc.data_ptr(), grad_w.data_ptr(),
                                ctypes.byref(d), int(flags), stream_ptr(feat.device)), "dfa_backward")
     return grad_feat, grad_loc, grad_w
 

@@ -6,6 +6,16 @@ from torch.autograd.function import Function, once_differentiable
 from .. import cabi
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _tables_i32(t):
     # the level tables arrive as int64 from feature_maps_format; cast once (tiny)
     return t if t.dtype == torch.int32 and t.is_contiguous() else t.contiguous().int()
@@ -23,6 +33,19 @@ class DeformableAggregationFunction(Function):
         scale_start_index = _tables_i32(scale_start_index)
         sampling_location = sampling_location.contiguous().float()
         weights = weights.contiguous().float()
+        ctx.grad_feat = ctx.grad_feat_ready = None
+        if ctx.needs_input_grad[0]:
+            # grad_mc_ms_feat is a scatter target and must start from zero (92 MB per sample at
+            # R50): zero it NOW on a side stream, so the fill overlaps this forward and whatever
+            # runs until the backward instead of sitting in front of the backward kernel.
+            cur, side = torch.cuda.current_stream(mc_ms_feat.device), _side_stream(mc_ms_feat.device)
+            ctx.grad_feat = torch.empty(mc_ms_feat.shape, device=mc_ms_feat.device, dtype=torch.float32)
+            side.wait_stream(cur)              # the allocator may hand out a block still in use on `cur`
+            with torch.cuda.stream(side):
+                ctx.grad_feat.zero_()
+                ctx.grad_feat_ready = torch.cuda.Event()
+                ctx.grad_feat_ready.record(side)
+            ctx.grad_feat.record_stream(side)
         output = cabi.forward(mc_ms_feat, spatial_shape, scale_start_index, sampling_location,
                               weights)
         ctx.save_for_backward(mc_ms_feat, spatial_shape, scale_start_index, sampling_location,
@@ -34,10 +57,19 @@ class DeformableAggregationFunction(Function):
     def backward(ctx, grad_output):
         mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights = ctx.saved_tensors
         # one memset (grad_feat) instead of the reference's three zeros_like (:55-57): the kernel
-        # writes the two small gradients in full
-        grad_feat, grad_loc, grad_w = cabi.backward(
-            mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights,
-            grad_output.contiguous().float())
-        if mc_ms_feat.dtype != torch.float32:
+        # writes the two small gradients in full; the one fill left was started in forward()
+        grad_feat, ctx.grad_feat = ctx.grad_feat, None
+        if grad_feat is not None:
+            torch.cuda.current_stream(mc_ms_feat.device).wait_event(ctx.grad_feat_ready)
+            grad_feat, grad_loc, grad_w = cabi.backward(
+                mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights,
+                grad_output.contiguous().float(), grad_feat=grad_feat,
+                grad_loc=torch.empty_like(sampling_location), grad_w=torch.empty_like(weights),
+                flags=cabi.BWD_OVERWRITE_SMALL)
+        else:   # frozen features (scatter skipped), or a second backward through a retained graph
+            grad_feat, grad_loc, grad_w = cabi.backward(
+                mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights,
+                grad_output.contiguous().float(), need_feat=ctx.needs_input_grad[0])
+        if grad_feat is not None and mc_ms_feat.dtype != torch.float32:
             grad_feat = grad_feat.to(mc_ms_feat.dtype)
         return grad_feat, None, None, grad_loc, grad_w

@@ -158,6 +158,23 @@ def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
             assert_close(out, ref, RTOL_F32, "variant %d %s" % (variant, dtype))
 
 
+@pytest.mark.parametrize("variant", [0, 10, 11, 12, 13])
+def test_every_backward_kernel_variant_vs_oracle(variant, monkeypatch):
+    """DFA_BWD_VARIANT: row-merging backward (tuning points) and the one-warp-per-group kernel, both
+    buffer contracts, fp32 and bf16 feature tables, sparse / dense / many-sample anchors."""
+    monkeypatch.setenv("DFA_BWD_VARIANT", str(variant))
+    from simpb_b200 import synthetic
+    cases = [synthetic.rig_op_inputs(bs=1, A=200, seed=31),
+             synthetic.op_inputs_uniform(bs=1, A=60, seed=32),
+             small_case(33, bs=2, A=17, P=13, K=6, sizes=SIZES3, C=256, G=8),
+             small_case(34, bs=1, A=9, P=5, K=2, sizes=SIZES3, C=128, G=8),
+             small_case(35, bs=1, A=5, P=3, K=3, sizes=SIZES3, C=256, G=8),     # odd P*K: no TMA
+             small_case(36, bs=1, A=3, P=40, K=6, sizes=SIZES3, C=256, G=8)]    # several rounds
+    for d in cases:
+        check_case(d)
+    check_case(cases[2], dtype=torch.bfloat16)
+
+
 def test_training_anchor_count_vs_oracle():
     from simpb_b200 import synthetic
     check_case(synthetic.rig_op_inputs(bs=1, A=1220, seed=4))
@@ -302,6 +319,31 @@ def test_autograd_function_and_torch_extension():
     assert torch.equal(gl, loc.grad) and torch.equal(gw, w.grad)
     with pytest.raises(RuntimeError):
         ext.deformable_aggregation_forward(g["feat"], g["shape"].long(), g["start"], g["loc"], g["w"])
+
+
+def test_frozen_features_skip_the_scatter_and_retained_graphs_work():
+    from simpb_b200 import cabi, deformable_aggregation_function
+    d = small_case(16, bs=2, A=12, P=13, K=6, sizes=SIZES3, C=256, G=8)
+    g = dev(d)
+    rgf, rgl, rgw = oracle.backward(d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"],
+                                    d["sampling_location"], d["weights"], d["grad_output"])
+    gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"], need_feat=False)
+    assert gf is None
+    assert_close(gl, rgl, RTOL_F32, "grad_loc without feature gradient")
+    assert_close(gw, rgw, RTOL_F32, "grad_weights without feature gradient")
+    # autograd: features frozen
+    loc = g["loc"].clone().requires_grad_(); w = g["w"].clone().requires_grad_()
+    deformable_aggregation_function(g["feat"], g["shape"], g["start"], loc, w).backward(g["go"])
+    assert_close(loc.grad, rgl, RTOL_F32, "autograd grad_loc (frozen features)")
+    # autograd: two backward passes through one retained graph (the pre-zeroed buffer is used once)
+    feat = g["feat"].clone().requires_grad_()
+    out = deformable_aggregation_function(feat, g["shape"], g["start"], g["loc"], g["w"])
+    out.backward(g["go"], retain_graph=True)
+    first = feat.grad.clone()
+    feat.grad = None
+    out.backward(g["go"])
+    assert_close(first, rgf, RTOL_F32, "grad_feat, first pass")
+    assert_close(feat.grad, rgf, RTOL_F32, "grad_feat, second pass")
 
 
 def test_runs_on_a_side_stream():
