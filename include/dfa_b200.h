@@ -20,6 +20,8 @@
  *   dfa_softmax_weights    models/blocks.py:175-195 (softmax over cams x levels x points, attn-drop
  *                          mask) + the permute of models/blocks.py:133-144
  *   dfa_softmax_weights_backward     autograd of the above
+ *   dfa_softmax_weights_split(_backward)  the same for models/blocks.py:166-174's camera-embedding
+ *                          branch, with the broadcast add folded into the kernel
  *   dfa_forward_host       the same forward, called with HOST buffers (copies inside)
  *
  * Tensor layouts (row-major, innermost last) — ops/src/deformable_aggregation.cpp:22-28:
@@ -131,6 +133,23 @@ int dfa_softmax_weights_backward(const float *logits, const uint8_t *keep_mask, 
                                  const float *grad_weights, float *grad_logits, int bs,
                                  int num_anchors, int num_cams, int num_scale, int num_pts,
                                  int num_groups, void *stream);
+
+/* The same with SPLIT logits.  weights_fc is linear, so with camera embedding
+ * weights_fc(feature[b,a] + cam[b,k]) = logits_anchor[b,a,:] + logits_cam[b,k,:]  with
+ * logits_anchor [bs,A,L*P*G] = weights_fc(feature) (bias included) and logits_cam [bs,K,L*P*G] =
+ * cam @ W^T: the module runs the GEMM on bs*(A+K) rows instead of bs*A*K and the two parts are
+ * added inside the kernel.  The backward writes grad_logits_full [bs,A,K,L*P*G] (the caller sums it
+ * over anchors for the camera part) and grad_logits_anchor [bs,A,L*P*G] (summed over cameras). */
+int dfa_softmax_weights_split(const float *logits_anchor, const float *logits_cam,
+                              const uint8_t *keep_mask, float scale, float *weights, int bs,
+                              int num_anchors, int num_cams, int num_scale, int num_pts,
+                              int num_groups, void *stream);
+int dfa_softmax_weights_split_backward(const float *logits_anchor, const float *logits_cam,
+                                       const uint8_t *keep_mask, float scale,
+                                       const float *grad_weights, float *grad_logits_full,
+                                       float *grad_logits_anchor, int bs, int num_anchors,
+                                       int num_cams, int num_scale, int num_pts, int num_groups,
+                                       void *stream);
 
 /* Forward with HOST buffers: host→device copies of all five inputs, the kernel, and the
  * device→host copy of the output, on `stream`, then a stream synchronise.  Host buffers should

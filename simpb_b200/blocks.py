@@ -72,6 +72,29 @@ class _SoftmaxWeights(Function):
         return g, None, None, None
 
 
+class _SoftmaxWeightsSplit(Function):
+    """The same for the camera-embedding branch (:166-174), using that weights_fc is linear:
+    weights_fc(feature[b,a] + cam[b,k]) = weights_fc(feature)[b,a] + (cam @ W^T)[b,k].  The GEMM then
+    runs on bs*(A+K) rows instead of bs*A*K, and neither the [bs,A,K,C] sum nor the 9 MB logits
+    tensor is ever materialised: the kernel adds the two parts while it reads them."""
+
+    @staticmethod
+    def forward(ctx, logits_anchor, logits_cam, dims, keep, scale):
+        logits_anchor = logits_anchor.contiguous().float()
+        logits_cam = logits_cam.contiguous().float()
+        ctx.dims, ctx.scale = dims, scale
+        ctx.save_for_backward(logits_anchor, logits_cam, keep)
+        return cabi.softmax_weights_split(logits_anchor, logits_cam, dims, keep, scale)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_w):
+        la, lk, keep = ctx.saved_tensors
+        ga, gk = cabi.softmax_weights_split_backward(la, lk, ctx.dims, keep, ctx.scale,
+                                                     grad_w.contiguous().float())
+        return ga, gk, None, None, None
+
+
 class SparseBox3DKeyPointsGenerator(nn.Module):
     """models/detection3d/blocks.py:157-222.  Inside DFA the fused kernel is used; calling the
     module directly returns the 3-D key points [bs, A, P, 3] like the reference (plain torch —
@@ -245,8 +268,14 @@ class DeformableFeatureAggregation(nn.Module):
             keep = keep.to(torch.uint8).contiguous()
             scale = 1.0 / (1.0 - self.attn_drop)
         dims = (bs, A, self.num_cams, self.num_levels, self.num_pts, self.num_groups)
-        w = _SoftmaxWeights.apply(self.weight_logits(instance_feature, anchor_embed, metas), dims,
-                                  keep, scale)
+        if self.camera_encoder is not None:
+            cam = self.camera_encoder(metas["projection_mat"][:, :, :3].reshape(bs, self.num_cams, -1))
+            w = _SoftmaxWeightsSplit.apply(self.weights_fc(instance_feature + anchor_embed),
+                                           nn.functional.linear(cam, self.weights_fc.weight),
+                                           dims, keep, scale)
+        else:
+            w = _SoftmaxWeights.apply(self.weight_logits(instance_feature, anchor_embed, metas), dims,
+                                      keep, scale)
         return loc, w
 
     def forward(self, instance_feature, anchor, anchor_embed, feature_maps, metas, **kwargs):

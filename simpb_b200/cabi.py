@@ -18,7 +18,8 @@ BWD_ACCUMULATE, BWD_OVERWRITE_SMALL, BWD_ZERO_GRAD_FEAT = 0, 1, 2
 # every symbol include/dfa_b200.h declares (tests check the library exports each of them)
 SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_forward", "dfa_backward", "dfa_debug_indices",
            "dfa_flatten_maps", "dfa_keypoints_project", "dfa_keypoints_project_backward",
-           "dfa_softmax_weights", "dfa_softmax_weights_backward",
+           "dfa_softmax_weights", "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
+           "dfa_softmax_weights_split_backward",
            "dfa_forward_host_workspace_bytes", "dfa_forward_host")
 
 
@@ -51,12 +52,16 @@ def _load():
     f32 = ctypes.c_float
     lib.dfa_softmax_weights.argtypes = [vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.dfa_softmax_weights_backward.argtypes = [vp, vp, f32, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.dfa_softmax_weights_split.argtypes = [vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.dfa_softmax_weights_split_backward.argtypes = [vp, vp, vp, f32, vp, vp, vp, i32, i32, i32, i32,
+                                                       i32, i32, vp]
     lib.dfa_forward_host_workspace_bytes.restype = i64
     lib.dfa_forward_host_workspace_bytes.argtypes = [i32, dp]
     lib.dfa_forward_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp, i64, vp]
     for name in ("dfa_forward", "dfa_backward", "dfa_debug_indices", "dfa_flatten_maps",
                  "dfa_keypoints_project", "dfa_keypoints_project_backward", "dfa_softmax_weights",
-                 "dfa_softmax_weights_backward", "dfa_forward_host"):
+                 "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
+                 "dfa_softmax_weights_split_backward", "dfa_forward_host"):
         getattr(lib, name).restype = i32
     return lib
 
@@ -295,6 +300,44 @@ def softmax_weights_backward(logits, dims, keep, scale, grad_w):
             grad_w.data_ptr(), g.data_ptr(), bs, A, K, L, P, G, stream_ptr(logits.device)),
             "dfa_softmax_weights_backward")
     return g
+
+
+def _split_args(logits_anchor, logits_cam, dims, keep):
+    _need(logits_anchor, "logits_anchor", torch.float32); _need(logits_cam, "logits_cam", torch.float32)
+    bs, A, K, L, P, G = dims
+    if logits_anchor.numel() != bs * A * L * P * G or logits_cam.numel() != bs * K * L * P * G:
+        raise DfaError("split logits must be [bs, A, L*P*G] and [bs, K, L*P*G]")
+    if keep is not None:
+        _need(keep, "keep_mask", torch.uint8)
+        if keep.numel() != bs * A * K * P:
+            raise DfaError("keep_mask must be uint8 [bs, A, K, P]")
+
+
+def softmax_weights_split(logits_anchor, logits_cam, dims, keep=None, scale=1.0):
+    """weights [bs,A,P,K,L,G] from logits_anchor [bs,A,L*P*G] + logits_cam [bs,K,L*P*G]."""
+    _split_args(logits_anchor, logits_cam, dims, keep)
+    bs, A, K, L, P, G = dims
+    w = torch.empty(bs, A, P, K, L, G, device=logits_anchor.device, dtype=torch.float32)
+    with torch.cuda.device(w.device):
+        check(lib.dfa_softmax_weights_split(
+            logits_anchor.data_ptr(), logits_cam.data_ptr(), keep.data_ptr() if keep is not None else None,
+            float(scale), w.data_ptr(), bs, A, K, L, P, G, stream_ptr(w.device)), "dfa_softmax_weights_split")
+    return w
+
+
+def softmax_weights_split_backward(logits_anchor, logits_cam, dims, keep, scale, grad_w):
+    """Returns (grad_logits_anchor [bs,A,L*P*G], grad_logits_cam [bs,K,L*P*G])."""
+    _split_args(logits_anchor, logits_cam, dims, keep)
+    _need(grad_w, "grad_weights", torch.float32)
+    bs, A, K, L, P, G = dims
+    g_full = torch.empty(bs, A, K, L * P * G, device=grad_w.device, dtype=torch.float32)
+    g_anchor = torch.empty_like(logits_anchor)
+    with torch.cuda.device(grad_w.device):
+        check(lib.dfa_softmax_weights_split_backward(
+            logits_anchor.data_ptr(), logits_cam.data_ptr(), keep.data_ptr() if keep is not None else None,
+            float(scale), grad_w.data_ptr(), g_full.data_ptr(), g_anchor.data_ptr(), bs, A, K, L, P, G,
+            stream_ptr(grad_w.device)), "dfa_softmax_weights_split_backward")
+    return g_anchor, g_full.sum(dim=1).reshape(logits_cam.shape)
 
 
 class HostForward:

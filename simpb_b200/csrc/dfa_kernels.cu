@@ -1748,8 +1748,23 @@ __global__ void __launch_bounds__(128)
 // K*L*P entries of each (b, a, g).  keep [bs, A, K, P] (uint8, may be NULL) is the attn-drop keep
 // mask of models/blocks.py:188-195 and `scale` its 1/(1-p).  One CTA per anchor; the anchor's
 // logits are staged in shared memory once.  Thread t owns group t % G (G divides the block).
+// Reduction over the threads that own the same group (tid % G, G a power of two <= 32 here): xor
+// shuffles inside the warp, then one shared-memory row per warp.
 template <int NT>
 __device__ __forceinline__ float group_reduce(float v, float *s_red, int tid, int G, bool is_max) {
+  if (G <= 32 && (G & (G - 1)) == 0) {
+    for (int m = G; m < 32; m <<= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, v, m);
+      v = is_max ? fmaxf(v, o) : v + o;
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane < G) s_red[warp * G + lane] = v;
+    __syncthreads();
+    float r = s_red[lane % G];
+    for (int w = 1; w < NT / 32; ++w) r = is_max ? fmaxf(r, s_red[w * G + lane % G]) : r + s_red[w * G + lane % G];
+    __syncthreads();
+    return r;
+  }
   s_red[tid] = v;
   __syncthreads();
   float r = s_red[tid % G];
@@ -1758,17 +1773,24 @@ __device__ __forceinline__ float group_reduce(float v, float *s_red, int tid, in
   return r;
 }
 
+// `logits_cam` (may be NULL) is the camera part of split logits: weights_fc is linear, so
+// weights_fc(feature[b,a] + camera_embed[b,k]) = weights_fc(feature[b,a]) + W * camera_embed[b,k];
+// the module then runs the GEMM on [bs*A] and [bs*K] rows instead of [bs*A*K] and this kernel adds
+// the two parts on the fly: logits = logits[b,a, e % (L*P*G)] + logits_cam[b, e].
 template <int NT>
 __global__ void __launch_bounds__(NT)
-    dfa_softmax_weights_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ keep,
-                               float scale, float *__restrict__ w, int K, int L, int P, int G) {
+    dfa_softmax_weights_kernel(const float *__restrict__ logits, const float *__restrict__ logits_cam,
+                               const uint8_t *__restrict__ keep, float scale, float *__restrict__ w,
+                               int A, int K, int L, int P, int G) {
   extern __shared__ __align__(16) float s_x[];  // N*G logits
   __shared__ float s_red[NT];
-  const int tid = threadIdx.x, N = K * L * P, n_el = N * G;
+  const int tid = threadIdx.x, N = K * L * P, n_el = N * G, lpg = L * P * G;
   const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
+  const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * lpg : logits + base;
+  const float *lk = logits_cam ? logits_cam + static_cast<size_t>(blockIdx.x / A) * n_el : nullptr;
   float mx = -INFINITY;
   for (int e = tid; e < n_el; e += NT) {
-    const float v = __ldg(logits + base + e);
+    const float v = lk ? __ldg(la + e % lpg) + __ldg(lk + e) : __ldg(la + e);
     s_x[e] = v;
     mx = fmaxf(mx, v);
   }
@@ -1792,20 +1814,25 @@ __global__ void __launch_bounds__(NT)
 }
 
 // grad_logits = y * (dy - sum_n dy_n y_n) with y = softmax(logits) recomputed and
-// dy = keep * scale * grad_w (read through the permutation).
+// dy = keep * scale * grad_w (read through the permutation).  With split logits the anchor part of
+// the gradient (sum over cameras) is also written: grad_anchor [bs,A,L*P*G]; the camera part is the
+// sum of grad_logits over anchors, left to the caller.
 template <int NT>
 __global__ void __launch_bounds__(NT)
-    dfa_softmax_weights_bwd_kernel(const float *__restrict__ logits, const uint8_t *__restrict__ keep,
-                                   float scale, const float *__restrict__ grad_w,
-                                   float *__restrict__ grad_logits, int K, int L, int P, int G) {
+    dfa_softmax_weights_bwd_kernel(const float *__restrict__ logits, const float *__restrict__ logits_cam,
+                                   const uint8_t *__restrict__ keep, float scale,
+                                   const float *__restrict__ grad_w, float *__restrict__ grad_logits,
+                                   float *__restrict__ grad_anchor, int A, int K, int L, int P, int G) {
   extern __shared__ __align__(16) float s_x[];  // N*G softmax values, then N*G dy
   __shared__ float s_red[NT];
-  const int tid = threadIdx.x, N = K * L * P, n_el = N * G;
+  const int tid = threadIdx.x, N = K * L * P, n_el = N * G, lpg = L * P * G;
   float *s_dy = s_x + n_el;
   const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
+  const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * lpg : logits + base;
+  const float *lk = logits_cam ? logits_cam + static_cast<size_t>(blockIdx.x / A) * n_el : nullptr;
   float mx = -INFINITY;
   for (int e = tid; e < n_el; e += NT) {
-    const float v = __ldg(logits + base + e);
+    const float v = lk ? __ldg(la + e % lpg) + __ldg(lk + e) : __ldg(la + e);
     s_x[e] = v;
     mx = fmaxf(mx, v);
   }
@@ -1830,7 +1857,19 @@ __global__ void __launch_bounds__(NT)
     dot = fmaf(dy, y, dot);
   }
   dot = group_reduce<NT>(dot, s_red, tid, G, false);
-  for (int e = tid; e < n_el; e += NT) grad_logits[base + e] = s_x[e] * (s_dy[e] - dot);
+  for (int e = tid; e < n_el; e += NT) {
+    const float gx = s_x[e] * (s_dy[e] - dot);
+    grad_logits[base + e] = gx;
+    s_dy[e] = gx;
+  }
+  if (grad_anchor) {
+    __syncthreads();
+    for (int r = tid; r < lpg; r += NT) {
+      float t = 0.f;
+      for (int k = 0; k < K; ++k) t += s_dy[k * lpg + r];
+      grad_anchor[static_cast<size_t>(blockIdx.x) * lpg + r] = t;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2309,7 +2348,23 @@ int dfa_softmax_weights(const float *logits, const uint8_t *keep_mask, float sca
   auto kern = dfa_softmax_weights_kernel<SOFTMAX_NT>;
   if (int rc = set_smem(kern, smem)) return rc;
   kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
-      logits, keep_mask, scale, weights, num_cams, num_scale, num_pts, num_groups);
+      logits, nullptr, keep_mask, scale, weights, num_anchors, num_cams, num_scale, num_pts, num_groups);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int dfa_softmax_weights_split(const float *logits_anchor, const float *logits_cam,
+                              const uint8_t *keep_mask, float scale, float *weights, int bs,
+                              int num_anchors, int num_cams, int num_scale, int num_pts,
+                              int num_groups, void *stream) {
+  if (!logits_anchor || !logits_cam || !weights) return DFA_ERR_NULL_POINTER;
+  uint32_t smem = 0;
+  const long long n = static_cast<long long>(bs) * num_anchors;
+  if (int rc = softmax_check(n, num_cams, num_scale, num_pts, num_groups, 1, &smem)) return rc;
+  auto kern = dfa_softmax_weights_kernel<SOFTMAX_NT>;
+  if (int rc = set_smem(kern, smem)) return rc;
+  kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
+      logits_anchor, logits_cam, keep_mask, scale, weights, num_anchors, num_cams, num_scale, num_pts,
+      num_groups);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -2324,7 +2379,27 @@ int dfa_softmax_weights_backward(const float *logits, const uint8_t *keep_mask, 
   auto kern = dfa_softmax_weights_bwd_kernel<SOFTMAX_NT>;
   if (int rc = set_smem(kern, smem)) return rc;
   kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
-      logits, keep_mask, scale, grad_weights, grad_logits, num_cams, num_scale, num_pts, num_groups);
+      logits, nullptr, keep_mask, scale, grad_weights, grad_logits, nullptr, num_anchors, num_cams,
+      num_scale, num_pts, num_groups);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int dfa_softmax_weights_split_backward(const float *logits_anchor, const float *logits_cam,
+                                       const uint8_t *keep_mask, float scale,
+                                       const float *grad_weights, float *grad_logits_full,
+                                       float *grad_logits_anchor, int bs, int num_anchors,
+                                       int num_cams, int num_scale, int num_pts, int num_groups,
+                                       void *stream) {
+  if (!logits_anchor || !logits_cam || !grad_weights || !grad_logits_full || !grad_logits_anchor)
+    return DFA_ERR_NULL_POINTER;
+  uint32_t smem = 0;
+  const long long n = static_cast<long long>(bs) * num_anchors;
+  if (int rc = softmax_check(n, num_cams, num_scale, num_pts, num_groups, 2, &smem)) return rc;
+  auto kern = dfa_softmax_weights_bwd_kernel<SOFTMAX_NT>;
+  if (int rc = set_smem(kern, smem)) return rc;
+  kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
+      logits_anchor, logits_cam, keep_mask, scale, grad_weights, grad_logits_full, grad_logits_anchor,
+      num_anchors, num_cams, num_scale, num_pts, num_groups);
   return static_cast<int>(cudaGetLastError());
 }
 
