@@ -124,6 +124,8 @@ def forward(feat, shape, start, loc, w, out=None):
     if out is None:
         out = torch.empty(d.batch_size, d.num_anchors, d.num_embeds, device=feat.device,
                           dtype=torch.float32)
+    if d.batch_size == 0 or d.num_anchors == 0:      # nothing to aggregate (the reference launches 0 threads)
+        return out
     with torch.cuda.device(feat.device):
         check(lib.dfa_forward(feat.data_ptr(), feat_dtype(feat), shape.data_ptr(), start.data_ptr(),
                               loc.data_ptr(), w.data_ptr(), out.data_ptr(), ctypes.byref(d),
@@ -160,6 +162,10 @@ def backward(feat, shape, start, loc, w, grad_out, grad_feat=None, grad_loc=None
     if (grad_feat is not None and grad_feat.numel() != feat.numel()) or grad_loc.numel() != loc.numel() \
             or grad_w.numel() != w.numel():
         raise DfaError("gradient buffer sizes do not match their inputs")
+    if d.batch_size == 0 or d.num_anchors == 0:      # empty batch / no anchors: no contribution
+        if grad_feat is not None and (flags & BWD_ZERO_GRAD_FEAT):
+            grad_feat.zero_()
+        return grad_feat, grad_loc, grad_w
     with torch.cuda.device(feat.device):
         check(lib.dfa_backward(feat.data_ptr(), feat_dtype(feat), shape.data_ptr(), start.data_ptr(),
                                loc.data_ptr(), w.data_ptr(), grad_out.data_ptr(),

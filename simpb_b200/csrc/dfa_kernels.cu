@@ -1776,41 +1776,76 @@ __device__ __forceinline__ float group_reduce(float v, float *s_red, int tid, in
 // `logits_cam` (may be NULL) is the camera part of split logits: weights_fc is linear, so
 // weights_fc(feature[b,a] + camera_embed[b,k]) = weights_fc(feature[b,a]) + W * camera_embed[b,k];
 // the module then runs the GEMM on [bs*A] and [bs*K] rows instead of [bs*A*K] and this kernel adds
-// the two parts on the fly: logits = logits[b,a, e % (L*P*G)] + logits_cam[b, e].
+// the two parts on the fly: logits[b,a,k,r,g] = logits[b,a,r,g] + logits_cam[b,k,r,g], r = (l,p).
+//
+// Thread t owns group t % G and the rows r = t / G, t / G + NT / G, ... of every camera, so the
+// loops need no integer division; the (k,l,p) -> (p,k,l) permutation and the keep mask come from a
+// small table built once per CTA.
+struct SoftmaxTables {
+  uint16_t *perm;  // row (k,l,p) -> output row (p*K + k)*L + l
+  uint8_t *keep;   // row (k,l,p) -> keep flag
+};
+
+template <int NT>
+__device__ __forceinline__ void softmax_tables(SoftmaxTables t, const uint8_t *kp, int tid, int K, int L,
+                                               int P) {
+  const int LP = L * P, N = K * LP;
+  for (int n = tid; n < N; n += NT) {
+    const int k = n / LP, r = n - k * LP, l = r / P, p = r - l * P;
+    t.perm[n] = static_cast<uint16_t>((p * K + k) * L + l);
+    t.keep[n] = kp ? kp[k * P + p] : 1;
+  }
+}
+
+// s_x[e] <- softmax numerators; returns 1 / sum for this thread's group
+template <int NT>
+__device__ __forceinline__ float softmax_stage(float *s_x, float *s_red, const float *la, const float *lk,
+                                               int tid, int K, int LP, int G) {
+  const int g = tid % G, r0 = tid / G, rs = NT / G;
+  float mx = -INFINITY;
+  for (int k = 0; k < K; ++k)
+    for (int r = r0; r < LP; r += rs) {
+      const int e = (k * LP + r) * G + g;
+      const float v = lk ? __ldg(la + r * G + g) + __ldg(lk + e) : __ldg(la + e);
+      s_x[e] = v;
+      mx = fmaxf(mx, v);
+    }
+  mx = group_reduce<NT>(mx, s_red, tid, G, true);
+  float sum = 0.f;
+  for (int k = 0; k < K; ++k)
+    for (int r = r0; r < LP; r += rs) {
+      const int e = (k * LP + r) * G + g;
+      const float v = expf(s_x[e] - mx);
+      s_x[e] = v;
+      sum += v;
+    }
+  sum = group_reduce<NT>(sum, s_red, tid, G, false);
+  return 1.f / sum;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT)
     dfa_softmax_weights_kernel(const float *__restrict__ logits, const float *__restrict__ logits_cam,
                                const uint8_t *__restrict__ keep, float scale, float *__restrict__ w,
                                int A, int K, int L, int P, int G) {
-  extern __shared__ __align__(16) float s_x[];  // N*G logits
+  extern __shared__ __align__(16) float s_x[];  // N*G logits, then the tables
   __shared__ float s_red[NT];
-  const int tid = threadIdx.x, N = K * L * P, n_el = N * G, lpg = L * P * G;
+  const int tid = threadIdx.x, LP = L * P, N = K * LP, n_el = N * G;
+  SoftmaxTables tb{reinterpret_cast<uint16_t *>(s_x + n_el), nullptr};
+  tb.keep = reinterpret_cast<uint8_t *>(tb.perm + N);
   const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
-  const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * lpg : logits + base;
+  const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * LP * G : logits + base;
   const float *lk = logits_cam ? logits_cam + static_cast<size_t>(blockIdx.x / A) * n_el : nullptr;
-  float mx = -INFINITY;
-  for (int e = tid; e < n_el; e += NT) {
-    const float v = lk ? __ldg(la + e % lpg) + __ldg(lk + e) : __ldg(la + e);
-    s_x[e] = v;
-    mx = fmaxf(mx, v);
-  }
-  mx = group_reduce<NT>(mx, s_red, tid, G, true);
-  float sum = 0.f;
-  for (int e = tid; e < n_el; e += NT) {
-    const float v = expf(s_x[e] - mx);
-    s_x[e] = v;
-    sum += v;
-  }
-  sum = group_reduce<NT>(sum, s_red, tid, G, false);
-  const float inv = 1.f / sum;
-  const uint8_t *kp = keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr;
-  for (int e = tid; e < n_el; e += NT) {
-    const int g = e % G, n = e / G;
-    const int p = n % P, kl = n / P, l = kl % L, k = kl / L;
-    float v = s_x[e] * inv;
-    if (kp) v = kp[k * P + p] ? v * scale : 0.f;
-    w[base + ((static_cast<size_t>(p) * K + k) * L + l) * G + g] = v;
-  }
+  softmax_tables<NT>(tb, keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr, tid, K, L, P);
+  const float inv = softmax_stage<NT>(s_x, s_red, la, lk, tid, K, LP, G);  // syncs inside: tables visible
+  const int g = tid % G, r0 = tid / G, rs = NT / G;
+  const float on = keep ? scale : 1.f;
+  for (int k = 0; k < K; ++k)
+    for (int r = r0; r < LP; r += rs) {
+      const int n = k * LP + r;
+      const float v = tb.keep[n] ? s_x[n * G + g] * inv * on : 0.f;
+      w[base + static_cast<size_t>(tb.perm[n]) * G + g] = v;
+    }
 }
 
 // grad_logits = y * (dy - sum_n dy_n y_n) with y = softmax(logits) recomputed and
@@ -1823,52 +1858,38 @@ __global__ void __launch_bounds__(NT)
                                    const uint8_t *__restrict__ keep, float scale,
                                    const float *__restrict__ grad_w, float *__restrict__ grad_logits,
                                    float *__restrict__ grad_anchor, int A, int K, int L, int P, int G) {
-  extern __shared__ __align__(16) float s_x[];  // N*G softmax values, then N*G dy
+  extern __shared__ __align__(16) float s_x[];  // N*G softmax values, N*G dy, then the tables
   __shared__ float s_red[NT];
-  const int tid = threadIdx.x, N = K * L * P, n_el = N * G, lpg = L * P * G;
+  const int tid = threadIdx.x, LP = L * P, N = K * LP, n_el = N * G;
   float *s_dy = s_x + n_el;
+  SoftmaxTables tb{reinterpret_cast<uint16_t *>(s_dy + n_el), nullptr};
+  tb.keep = reinterpret_cast<uint8_t *>(tb.perm + N);
   const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
-  const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * lpg : logits + base;
+  const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * LP * G : logits + base;
   const float *lk = logits_cam ? logits_cam + static_cast<size_t>(blockIdx.x / A) * n_el : nullptr;
-  float mx = -INFINITY;
-  for (int e = tid; e < n_el; e += NT) {
-    const float v = lk ? __ldg(la + e % lpg) + __ldg(lk + e) : __ldg(la + e);
-    s_x[e] = v;
-    mx = fmaxf(mx, v);
-  }
-  mx = group_reduce<NT>(mx, s_red, tid, G, true);
-  float sum = 0.f;
-  for (int e = tid; e < n_el; e += NT) {
-    const float v = expf(s_x[e] - mx);
-    s_x[e] = v;
-    sum += v;
-  }
-  sum = group_reduce<NT>(sum, s_red, tid, G, false);
-  const float inv = 1.f / sum;
-  const uint8_t *kp = keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr;
+  softmax_tables<NT>(tb, keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr, tid, K, L, P);
+  const float inv = softmax_stage<NT>(s_x, s_red, la, lk, tid, K, LP, G);
+  const int g = tid % G, r0 = tid / G, rs = NT / G;
+  const float on = keep ? scale : 1.f;
   float dot = 0.f;
-  for (int e = tid; e < n_el; e += NT) {
-    const int g = e % G, n = e / G;
-    const int p = n % P, kl = n / P, l = kl % L, k = kl / L;
-    float dy = __ldg(grad_w + base + ((static_cast<size_t>(p) * K + k) * L + l) * G + g);
-    if (kp) dy = kp[k * P + p] ? dy * scale : 0.f;
-    const float y = s_x[e] * inv;
-    s_x[e] = y, s_dy[e] = dy;
-    dot = fmaf(dy, y, dot);
-  }
-  dot = group_reduce<NT>(dot, s_red, tid, G, false);
-  for (int e = tid; e < n_el; e += NT) {
-    const float gx = s_x[e] * (s_dy[e] - dot);
-    grad_logits[base + e] = gx;
-    s_dy[e] = gx;
-  }
-  if (grad_anchor) {
-    __syncthreads();
-    for (int r = tid; r < lpg; r += NT) {
-      float t = 0.f;
-      for (int k = 0; k < K; ++k) t += s_dy[k * lpg + r];
-      grad_anchor[static_cast<size_t>(blockIdx.x) * lpg + r] = t;
+  for (int k = 0; k < K; ++k)
+    for (int r = r0; r < LP; r += rs) {
+      const int n = k * LP + r, e = n * G + g;
+      const float dy = tb.keep[n] ? __ldg(grad_w + base + static_cast<size_t>(tb.perm[n]) * G + g) * on : 0.f;
+      const float y = s_x[e] * inv;
+      s_x[e] = y, s_dy[e] = dy;
+      dot = fmaf(dy, y, dot);
     }
+  dot = group_reduce<NT>(dot, s_red, tid, G, false);
+  for (int r = r0; r < LP; r += rs) {
+    float t = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int e = (k * LP + r) * G + g;
+      const float gx = s_x[e] * (s_dy[e] - dot);
+      grad_logits[base + e] = gx;
+      t += gx;
+    }
+    if (grad_anchor) grad_anchor[static_cast<size_t>(blockIdx.x) * LP * G + r * G + g] = t;
   }
 }
 
@@ -2331,7 +2352,8 @@ constexpr int SOFTMAX_NT = 256;
 int softmax_check(long long n_anchors, int K, int L, int P, int G, long long smem_floats, uint32_t *smem) {
   if (n_anchors <= 0 || K <= 0 || L <= 0 || P <= 0 || G <= 0) return DFA_ERR_BAD_DIMS;
   if (n_anchors >= (1ll << 31) || SOFTMAX_NT % G != 0) return DFA_ERR_UNSUPPORTED;
-  const long long bytes = 4ll * K * L * P * G * smem_floats;
+  if (static_cast<long long>(K) * L * P >= 65536) return DFA_ERR_UNSUPPORTED;  // 16-bit row table
+  const long long bytes = 4ll * K * L * P * G * smem_floats + 3ll * K * L * P + 16;
   if (bytes > 200ll * 1024) return DFA_ERR_UNSUPPORTED;
   *smem = static_cast<uint32_t>(bytes);
   return 0;

@@ -226,6 +226,69 @@ def test_all_samples_masked_gives_zeros():
     assert (gf == 0).all() and (gl == 0).all() and (gw == 0).all()
 
 
+def test_empty_inputs():
+    """No anchors / empty batch: the reference launches zero threads and returns empty tensors."""
+    from simpb_b200 import cabi, deformable_aggregation_function
+    d = small_case(8, bs=2, A=3, P=3, K=2, sizes=SIZES3, C=64, G=8)
+    g = dev(d)
+    out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"][:, :0].contiguous(),
+                       g["w"][:, :0].contiguous())
+    assert tuple(out.shape) == (2, 0, 64)
+    gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"][:, :0].contiguous(),
+                               g["w"][:, :0].contiguous(), g["go"][:, :0].contiguous())
+    assert tuple(gl.shape) == (2, 0, 3, 2, 2) and float(gf.abs().max()) == 0.0
+    out = deformable_aggregation_function(g["feat"][:0], g["shape"], g["start"], g["loc"][:0], g["w"][:0])
+    assert tuple(out.shape) == (0, 3, 64)
+
+
+def test_single_anchor_single_point_single_camera():
+    check_case(small_case(9, bs=1, A=1, P=1, K=1, sizes=((3, 5),), C=8, G=8))   # 1 channel per group
+    check_case(small_case(10, bs=1, A=1, P=2, K=1, sizes=((1, 1),), C=256, G=8))  # 1x1 feature map
+
+
+def test_r101_shape_vs_oracle():
+    """BASELINE.json config #4: 1408x512 maps (359,040 rows per sample), forward and the two small
+    gradients against the oracle; the feature gradient through its adjoint identity."""
+    from simpb_b200 import cabi, synthetic
+    d = synthetic.rig_op_inputs(bs=1, A=900, levels=synthetic.R101_LEVELS, seed=17)
+    g = dev(d)
+    out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    ref = oracle.forward(d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"],
+                         d["sampling_location"], d["weights"])
+    assert_close(out, ref, RTOL_F32, "R101 forward")
+    _, rgl, rgw = oracle.backward(d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"],
+                                  d["sampling_location"], d["weights"], d["grad_output"], need_feat=False)
+    gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    assert_close(gl, rgl, RTOL_F32, "R101 grad_loc")
+    assert_close(gw, rgw, RTOL_F32, "R101 grad_weights")
+    # out is linear in the features: <out, go> == <feat, grad_feat>
+    lhs = (torch.from_numpy(ref) * d["grad_output"].double()).sum()
+    rhs = (g["feat"].double() * gf.double()).sum().cpu()
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+
+
+def test_feature_maps_format_camera_groups_with_different_resolutions():
+    """ops/__init__.py:56-61: a list of per-group lists is formatted group by group and concatenated."""
+    from simpb_b200 import cabi, feature_maps_format
+    gen = torch.Generator().manual_seed(4)
+    grp_a = [torch.randn(2, 2, 16, h, w, generator=gen) for h, w in ((8, 12), (4, 6))]
+    grp_b = [torch.randn(2, 1, 16, h, w, generator=gen) for h, w in ((6, 10), (3, 5))]
+    col, shape, start = feature_maps_format([[m.cuda() for m in grp_a], [m.cuda() for m in grp_b]])
+    ca, sa, _ = module_ref.flatten_feature_maps(grp_a)
+    cb, sb, _ = module_ref.flatten_feature_maps(grp_b)
+    assert torch.equal(col.cpu(), torch.cat([ca, cb], dim=1))
+    assert torch.equal(shape.cpu(), torch.cat([sa, sb], dim=0))
+    assert start.cpu().flatten().tolist() == [0, 96, 120, 216, 240, 300]
+    # the op consumes the ragged table: sample the third camera (group b) at its first level's centre
+    loc = torch.full((2, 1, 1, 3, 2), -1.0)
+    loc[:, :, :, 2] = 0.5
+    w = torch.zeros(2, 1, 1, 3, 2, 1)
+    w[:, :, :, 2, 0] = 1.0
+    out = cabi.forward(col, shape.int(), start.int(), loc.cuda(), w.cuda())
+    ref = oracle.forward(col.cpu(), shape.cpu(), start.cpu(), loc, w)
+    assert_close(out, ref, RTOL_F32, "ragged camera groups")
+
+
 def test_border_values_are_excluded():
     """loc exactly 0 or 1 is masked (exclusive test, …_cuda.cu:168-171)."""
     from simpb_b200 import cabi
