@@ -1893,6 +1893,145 @@ __global__ void __launch_bounds__(NT)
   }
 }
 
+// Vectorised forms for G % 4 == 0 (SimPB: G = 8): a thread owns FOUR consecutive groups of a row
+// (one 16-byte load / store), threads t and t + Q share their groups (Q = G / 4 quads per row).
+// Same staging and tables as above; a quarter of the instructions.
+template <int NT>
+__device__ __forceinline__ float4 quad_reduce(float4 v, float4 *s_red4, int tid, int Q, bool is_max) {
+  // Q is a power of two <= 8 here: lanes with equal tid % Q combine by xor shuffles, warps via smem
+  auto comb = [is_max](float a, float b) { return is_max ? fmaxf(a, b) : a + b; };
+  for (int m = Q; m < 32; m <<= 1) {
+    v.x = comb(v.x, __shfl_xor_sync(0xffffffffu, v.x, m));
+    v.y = comb(v.y, __shfl_xor_sync(0xffffffffu, v.y, m));
+    v.z = comb(v.z, __shfl_xor_sync(0xffffffffu, v.z, m));
+    v.w = comb(v.w, __shfl_xor_sync(0xffffffffu, v.w, m));
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane < Q) s_red4[warp * Q + lane] = v;
+  __syncthreads();
+  float4 r = s_red4[lane % Q];
+  for (int w = 1; w < NT / 32; ++w) {
+    const float4 o = s_red4[w * Q + lane % Q];
+    r.x = comb(r.x, o.x), r.y = comb(r.y, o.y), r.z = comb(r.z, o.z), r.w = comb(r.w, o.w);
+  }
+  __syncthreads();
+  return r;
+}
+
+// numerators into s_x4, returns 1/sum for the thread's four groups
+template <int NT>
+__device__ __forceinline__ float4 softmax_stage4(float4 *s_x4, float4 *s_red4, const float4 *la,
+                                                 const float4 *lk, int tid, int K, int LP, int Q) {
+  const int q = tid % Q, r0 = tid / Q, rs = NT / Q;
+  float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int k = 0; k < K; ++k)
+    for (int r = r0; r < LP; r += rs) {
+      const int e = (k * LP + r) * Q + q;
+      float4 v;
+      if (lk) {
+        const float4 a = __ldg(la + r * Q + q), c = __ldg(lk + e);
+        v = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+      } else {
+        v = __ldg(la + e);
+      }
+      s_x4[e] = v;
+      mx = make_float4(fmaxf(mx.x, v.x), fmaxf(mx.y, v.y), fmaxf(mx.z, v.z), fmaxf(mx.w, v.w));
+    }
+  mx = quad_reduce<NT>(mx, s_red4, tid, Q, true);
+  float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < K; ++k)
+    for (int r = r0; r < LP; r += rs) {
+      const int e = (k * LP + r) * Q + q;
+      float4 v = s_x4[e];
+      v = make_float4(expf(v.x - mx.x), expf(v.y - mx.y), expf(v.z - mx.z), expf(v.w - mx.w));
+      s_x4[e] = v;
+      sum.x += v.x, sum.y += v.y, sum.z += v.z, sum.w += v.w;
+    }
+  sum = quad_reduce<NT>(sum, s_red4, tid, Q, false);
+  return make_float4(1.f / sum.x, 1.f / sum.y, 1.f / sum.z, 1.f / sum.w);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    dfa_softmax_weights4_kernel(const float *__restrict__ logits, const float *__restrict__ logits_cam,
+                                const uint8_t *__restrict__ keep, float scale, float *__restrict__ w,
+                                int A, int K, int L, int P, int G) {
+  extern __shared__ __align__(16) float s_x[];
+  __shared__ float4 s_red4[NT / 32 * 8];
+  const int tid = threadIdx.x, LP = L * P, N = K * LP, n_el = N * G, Q = G / 4;
+  float4 *s_x4 = reinterpret_cast<float4 *>(s_x);
+  SoftmaxTables tb{reinterpret_cast<uint16_t *>(s_x + n_el), nullptr};
+  tb.keep = reinterpret_cast<uint8_t *>(tb.perm + N);
+  const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
+  const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * LP * G : logits + base;
+  const float *lk = logits_cam ? logits_cam + static_cast<size_t>(blockIdx.x / A) * n_el : nullptr;
+  softmax_tables<NT>(tb, keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr, tid, K, L, P);
+  const float4 inv = softmax_stage4<NT>(s_x4, s_red4, reinterpret_cast<const float4 *>(la),
+                                        reinterpret_cast<const float4 *>(lk), tid, K, LP, Q);
+  const int q = tid % Q, r0 = tid / Q, rs = NT / Q;
+  const float on = keep ? scale : 1.f;
+  float4 *w4 = reinterpret_cast<float4 *>(w + base);
+  for (int k = 0; k < K; ++k)
+    for (int r = r0; r < LP; r += rs) {
+      const int n = k * LP + r;
+      const float4 v = s_x4[n * Q + q];
+      const float m = tb.keep[n] ? on : 0.f;
+      w4[static_cast<size_t>(tb.perm[n]) * Q + q] =
+          make_float4(v.x * inv.x * m, v.y * inv.y * m, v.z * inv.z * m, v.w * inv.w * m);
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+    dfa_softmax_weights4_bwd_kernel(const float *__restrict__ logits, const float *__restrict__ logits_cam,
+                                    const uint8_t *__restrict__ keep, float scale,
+                                    const float *__restrict__ grad_w, float *__restrict__ grad_logits,
+                                    float *__restrict__ grad_anchor, int A, int K, int L, int P, int G) {
+  extern __shared__ __align__(16) float s_x[];
+  __shared__ float4 s_red4[NT / 32 * 8];
+  const int tid = threadIdx.x, LP = L * P, N = K * LP, n_el = N * G, Q = G / 4;
+  float4 *s_x4 = reinterpret_cast<float4 *>(s_x), *s_dy4 = s_x4 + N * Q;
+  SoftmaxTables tb{reinterpret_cast<uint16_t *>(s_x + 2 * n_el), nullptr};
+  tb.keep = reinterpret_cast<uint8_t *>(tb.perm + N);
+  const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
+  const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * LP * G : logits + base;
+  const float *lk = logits_cam ? logits_cam + static_cast<size_t>(blockIdx.x / A) * n_el : nullptr;
+  softmax_tables<NT>(tb, keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr, tid, K, L, P);
+  const float4 inv = softmax_stage4<NT>(s_x4, s_red4, reinterpret_cast<const float4 *>(la),
+                                        reinterpret_cast<const float4 *>(lk), tid, K, LP, Q);
+  const int q = tid % Q, r0 = tid / Q, rs = NT / Q;
+  const float on = keep ? scale : 1.f;
+  const float4 *gw4 = reinterpret_cast<const float4 *>(grad_w + base);
+  float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < K; ++k)
+    for (int r = r0; r < LP; r += rs) {
+      const int n = k * LP + r, e = n * Q + q;
+      float4 dy = __ldg(gw4 + static_cast<size_t>(tb.perm[n]) * Q + q);
+      const float m = tb.keep[n] ? on : 0.f;
+      dy = make_float4(dy.x * m, dy.y * m, dy.z * m, dy.w * m);
+      float4 y = s_x4[e];
+      y = make_float4(y.x * inv.x, y.y * inv.y, y.z * inv.z, y.w * inv.w);
+      s_x4[e] = y, s_dy4[e] = dy;
+      dot.x = fmaf(dy.x, y.x, dot.x), dot.y = fmaf(dy.y, y.y, dot.y);
+      dot.z = fmaf(dy.z, y.z, dot.z), dot.w = fmaf(dy.w, y.w, dot.w);
+    }
+  dot = quad_reduce<NT>(dot, s_red4, tid, Q, false);
+  float4 *gl4 = reinterpret_cast<float4 *>(grad_logits + base);
+  for (int r = r0; r < LP; r += rs) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+      const int e = (k * LP + r) * Q + q;
+      const float4 y = s_x4[e], dy = s_dy4[e];
+      const float4 gx = make_float4(y.x * (dy.x - dot.x), y.y * (dy.y - dot.y), y.z * (dy.z - dot.z),
+                                    y.w * (dy.w - dot.w));
+      gl4[e] = gx;
+      t.x += gx.x, t.y += gx.y, t.z += gx.z, t.w += gx.w;
+    }
+    if (grad_anchor)
+      reinterpret_cast<float4 *>(grad_anchor + static_cast<size_t>(blockIdx.x) * LP * G)[r * Q + q] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1997,7 +2136,7 @@ int rows_vpr(const Dims &d, const void *feat, int nt) {
   constexpr int VEC = FeatVec<T>::VEC;
   if (d.C % VEC != 0 || (d.C / d.G) % VEC != 0 || !aligned(feat, 16)) return 0;
   const int vpr = d.C / VEC;
-  if (vpr > nt || (vpr & (vpr - 1)) != 0) return 0;
+  if (vpr > nt || nt % vpr != 0 || (vpr & (vpr - 1)) != 0) return 0;
   if (static_cast<long long>(d.num_feat) * d.C * static_cast<long long>(sizeof(T)) >= (1ll << 32)) return 0;
   return vpr;
 }
@@ -2078,7 +2217,7 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   }
   const int rvariant = variant >= 10 ? 1 : variant;
   if (rvariant >= 1) {
-    const int nt = rvariant >= 3 ? 512 : 256;
+    const int nt = rvariant == 5 ? 192 : rvariant == 6 ? 128 : rvariant >= 3 ? 512 : 256;
     const int vpr = rows_vpr<T>(d, feat, nt);
     if (vpr) {
       const bool tma = tma_ok(d, loc, w);
@@ -2091,6 +2230,8 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
         case 1: return ROWS(1, 256, 6);
         case 2: return ROWS(2, 256, 4);
         case 3: return ROWS(1, 512, 3);
+        case 5: return ROWS(1, 192, 8);
+        case 6: return ROWS(1, 128, 12);
         default: return ROWS(2, 512, 2);
       }
 #undef ROWS
@@ -2349,6 +2490,11 @@ int dfa_keypoints_project_backward(const float *anchor, const float *fix_scale, 
 
 namespace {
 constexpr int SOFTMAX_NT = 256;
+inline bool softmax_vec_ok(int G, const void *a, const void *b, const void *c, const void *e) {
+  const int Q = G / 4;
+  return G % 4 == 0 && (Q & (Q - 1)) == 0 && Q <= 8 && aligned(a, 16) && aligned(b, 16) &&
+         aligned(c, 16) && aligned(e, 16);
+}
 int softmax_check(long long n_anchors, int K, int L, int P, int G, long long smem_floats, uint32_t *smem) {
   if (n_anchors <= 0 || K <= 0 || L <= 0 || P <= 0 || G <= 0) return DFA_ERR_BAD_DIMS;
   if (n_anchors >= (1ll << 31) || SOFTMAX_NT % G != 0) return DFA_ERR_UNSUPPORTED;
@@ -2367,7 +2513,9 @@ int dfa_softmax_weights(const float *logits, const uint8_t *keep_mask, float sca
   uint32_t smem = 0;
   const long long n = static_cast<long long>(bs) * num_anchors;
   if (int rc = softmax_check(n, num_cams, num_scale, num_pts, num_groups, 1, &smem)) return rc;
-  auto kern = dfa_softmax_weights_kernel<SOFTMAX_NT>;
+  auto kern = softmax_vec_ok(num_groups, logits, weights, nullptr, nullptr)
+                  ? dfa_softmax_weights4_kernel<SOFTMAX_NT>
+                  : dfa_softmax_weights_kernel<SOFTMAX_NT>;
   if (int rc = set_smem(kern, smem)) return rc;
   kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
       logits, nullptr, keep_mask, scale, weights, num_anchors, num_cams, num_scale, num_pts, num_groups);
@@ -2382,7 +2530,9 @@ int dfa_softmax_weights_split(const float *logits_anchor, const float *logits_ca
   uint32_t smem = 0;
   const long long n = static_cast<long long>(bs) * num_anchors;
   if (int rc = softmax_check(n, num_cams, num_scale, num_pts, num_groups, 1, &smem)) return rc;
-  auto kern = dfa_softmax_weights_kernel<SOFTMAX_NT>;
+  auto kern = softmax_vec_ok(num_groups, logits_anchor, logits_cam, weights, nullptr)
+                  ? dfa_softmax_weights4_kernel<SOFTMAX_NT>
+                  : dfa_softmax_weights_kernel<SOFTMAX_NT>;
   if (int rc = set_smem(kern, smem)) return rc;
   kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
       logits_anchor, logits_cam, keep_mask, scale, weights, num_anchors, num_cams, num_scale, num_pts,
@@ -2398,7 +2548,9 @@ int dfa_softmax_weights_backward(const float *logits, const uint8_t *keep_mask, 
   uint32_t smem = 0;
   const long long n = static_cast<long long>(bs) * num_anchors;
   if (int rc = softmax_check(n, num_cams, num_scale, num_pts, num_groups, 2, &smem)) return rc;
-  auto kern = dfa_softmax_weights_bwd_kernel<SOFTMAX_NT>;
+  auto kern = softmax_vec_ok(num_groups, logits, grad_weights, grad_logits, nullptr)
+                  ? dfa_softmax_weights4_bwd_kernel<SOFTMAX_NT>
+                  : dfa_softmax_weights_bwd_kernel<SOFTMAX_NT>;
   if (int rc = set_smem(kern, smem)) return rc;
   kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
       logits, nullptr, keep_mask, scale, grad_weights, grad_logits, nullptr, num_anchors, num_cams,
@@ -2417,7 +2569,10 @@ int dfa_softmax_weights_split_backward(const float *logits_anchor, const float *
   uint32_t smem = 0;
   const long long n = static_cast<long long>(bs) * num_anchors;
   if (int rc = softmax_check(n, num_cams, num_scale, num_pts, num_groups, 2, &smem)) return rc;
-  auto kern = dfa_softmax_weights_bwd_kernel<SOFTMAX_NT>;
+  auto kern = softmax_vec_ok(num_groups, logits_anchor, logits_cam, grad_weights, grad_logits_full) &&
+                      aligned(grad_logits_anchor, 16)
+                  ? dfa_softmax_weights4_bwd_kernel<SOFTMAX_NT>
+                  : dfa_softmax_weights_bwd_kernel<SOFTMAX_NT>;
   if (int rc = set_smem(kern, smem)) return rc;
   kern<<<static_cast<int>(n), SOFTMAX_NT, smem, static_cast<cudaStream_t>(stream)>>>(
       logits_anchor, logits_cam, keep_mask, scale, grad_weights, grad_logits_full, grad_logits_anchor,
