@@ -1,6 +1,7 @@
 """In-tree build of the native code (sm_100a only).
 
-  libdfa_b200.so                          CUDA kernels + the C ABI of include/dfa_b200.h (nvcc)
+  libdfa_b200.so                          CUDA kernels + the C ABI of include/dfa_b200.h (nvcc; three
+                                          translation units under csrc/, compiled in parallel)
   ops/deformable_aggregation_ext*.so      thin torch extension with the reference's two entry
                                           points, forwarding raw pointers to the C ABI (g++)
 
@@ -14,13 +15,16 @@ import sysconfig
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libdfa_b200.so")
-KERNEL_SRC = os.path.join(PKG, "csrc", "dfa_kernels.cu")
+KERNEL_SRCS = [os.path.join(PKG, "csrc", n) for n in ("dfa_forward.cu", "dfa_backward.cu", "dfa_frontend.cu")]
+COMMON_HDR = os.path.join(PKG, "csrc", "dfa_common.cuh")
+OBJ_DIR = os.path.join(PKG, "csrc", "build")
 EXT_SRC = os.path.join(PKG, "csrc", "dfa_torch_ext.cpp")
 HEADER = os.path.join(ROOT, "include", "dfa_b200.h")
 EXT = os.path.join(PKG, "ops", "deformable_aggregation_ext" + sysconfig.get_config_var("EXT_SUFFIX"))
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "--cudart", "shared"]
+              "-Xcompiler", "-fPIC"]
+LINK_FLAGS = ["-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a"]
 
 
 def _stale(target, sources):
@@ -35,14 +39,38 @@ def _run(cmd):
     return r
 
 
-def build_lib(force=False, verbose=False):
-    if force or _stale(LIB, [KERNEL_SRC, HEADER]):
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB, KERNEL_SRC]
+def compile_objects(extra_flags=(), obj_dir=OBJ_DIR, verbose=False):
+    """nvcc -c of every translation unit, in parallel; returns (object paths, ptxas stderr)."""
+    os.makedirs(obj_dir, exist_ok=True)
+    procs = []
+    for src in KERNEL_SRCS:
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-c",
+                                                           "-o", obj, src]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        r = _run(cmd)
+        procs.append((obj, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs, log = [], ""
+    for obj, cmd, p in procs:
+        out, err = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("build failed: %s\n%s%s" % (" ".join(cmd), out[-4000:], err[-4000:]))
+        objs.append(obj)
+        log += err
+    return objs, log
+
+
+def link_lib(objs, target=LIB):
+    _run(["nvcc"] + LINK_FLAGS + ["-o", target] + objs)
+    return target
+
+
+def build_lib(force=False, verbose=False):
+    if force or _stale(LIB, KERNEL_SRCS + [COMMON_HDR, HEADER]):
+        objs, log = compile_objects(verbose=verbose)
+        link_lib(objs)
         if verbose:
-            print(r.stderr, file=sys.stderr)
+            print(log, file=sys.stderr)
     return LIB
 
 

@@ -1,0 +1,956 @@
+// dfa_forward.cu — forward kernels of the deformable feature aggregation and their C ABI
+// (dfa_forward, dfa_forward_host, dfa_debug_indices).  See DESIGN.md §4.1.
+//
+// One CTA owns one anchor (b, a).  Its sampling locations (P*K*2 floats) and weights (P*K*L*G
+// floats) are contiguous per anchor and are staged into shared memory with TMA bulk copies
+// (cp.async.bulk -> UBLKCP) completing on mbarriers; warp 0 compacts the samples that pass the op's
+// exclusive (0,1) test.  Three kernel families follow, selected by shape (and DFA_FWD_VARIANT):
+// row-sliced (default), row-merging, one warp per group; plus a shape-generic fallback.
+// The weighted sum lives in registers and the output row is written once: no atomics and no
+// zero-filled output (the reference: one float atomic per thread on an at::zeros tensor).
+#include "dfa_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+// T: feature element type.  LPG: lanes per group row = (C/G)*sizeof(T)/16.  U: taps in flight
+// per lane.  Block = 32*G threads (warp g = group g).
+template <typename T, int LPG, int U, bool TMA, int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256) ? ((sizeof(T) == 4 ? 1536 : 1024) / MAXT) : 1)
+    dfa_fwd_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                   const int *__restrict__ start, const float *__restrict__ loc,
+                   const float *__restrict__ weights, float *__restrict__ out, Dims d) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  constexpr int TPW = 32 / (4 * LPG);  // taps one warp instruction covers
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, TPW * U, false);
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  TapQ *s_rec = reinterpret_cast<TapQ *>(smem + lay.rec);
+  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  int *s_list = reinterpret_cast<int *>(smem + lay.list);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int anchor = blockIdx.x;  // b * A + a
+  const int b = anchor / d.A;
+  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
+
+  const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
+                                        weights + static_cast<size_t>(anchor) * wcount, s_w,
+                                        s_loc, s_list, bars, s_nvalid, PK, wcount);
+  const int ntaps = nv * d.L;
+  const int ntaps_pad = (ntaps + TPW * U - 1) / (TPW * U) * (TPW * U);
+
+  // tap records, level-major so that the coarse levels' shared rows are touched back to back
+  for (int t = tid; t < ntaps_pad; t += blockDim.x) {
+    TapQ r[4] = {{-1, 0.f}, {-1, 0.f}, {-1, 0.f}, {-1, 0.f}};
+    int widx = 0;
+    if (t < ntaps) {
+      const int l = t / nv, i = t - l * nv;
+      const int s = s_list[i];
+      const int k = s % d.K;
+      const int kl = k * d.L + l;
+      const int H = __ldg(shape + 2 * kl), W = __ldg(shape + 2 * kl + 1);
+      TapGeom gm;
+      tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], H, W, __ldg(start + kl), gm);
+      const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (gm.row[q] >= 0) r[q].off = gm.row[q] * d.C, r[q].bw = bw[q];
+      widx = (s * d.L + l) * d.G;
+    }
+    int4 *dst = reinterpret_cast<int4 *>(s_rec + 4 * t);
+    dst[0] = make_int4(r[0].off, __float_as_int(r[0].bw), r[1].off, __float_as_int(r[1].bw));
+    dst[1] = make_int4(r[2].off, __float_as_int(r[2].bw), r[3].off, __float_as_int(r[3].bw));
+    s_widx[t] = widx;
+  }
+  __syncthreads();
+  if (TMA) mbar_wait(&bars[1], 0);  // weights have landed
+
+  const int j = lane % LPG, q = (lane / LPG) & 3, sub = lane / (4 * LPG);
+  const int cpg = d.C / d.G;
+  const T *fb = feat + static_cast<size_t>(b) * d.num_feat * d.C + g * cpg + j * VEC;
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+
+  for (int t0 = 0; t0 < ntaps_pad; t0 += TPW * U) {
+    float v[U][VEC], cw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * TPW + sub;
+      const int2 rq = *reinterpret_cast<const int2 *>(s_rec + 4 * t + q);
+      const float wgt = s_w[s_widx[t] + g];
+      if (rq.x >= 0) {
+        cw[u] = __int_as_float(rq.y) * wgt;
+        FeatVec<T>::load(fb + rq.x, v[u]);
+      } else {  // corner outside the map (zero padding) or padding tap: contributes nothing
+        cw[u] = 0.f;
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) v[u][c] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) acc[c] = fmaf(cw[u], v[u][c], acc[c]);
+  }
+  // fold corners (and sub-taps): lanes differing in bits >= log2(LPG)
+#pragma unroll
+  for (int m = LPG; m < 32; m <<= 1)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], m);
+  if (lane < LPG) {
+    float4 *o = reinterpret_cast<float4 *>(out + static_cast<size_t>(anchor) * d.C + g * cpg + j * VEC);
+#pragma unroll
+    for (int c = 0; c < VEC / 4; ++c)
+      o[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// forward, row-sliced mapping
+// ------------------------------------------------------------------------------------------
+// A feature row (C channels) is `vpr` 16-byte vectors.  The CTA is split into NT/vpr slices;
+// slice s owns taps s, s+slices, ... and inside a slice thread v owns vector v of the row, i.e.
+// VEC consecutive channels of ONE group, for all four corners of the tap.  Per tap a thread
+// issues four 128-bit loads (a warp covers 512 contiguous bytes of each corner row), reads the
+// tap record with two broadcast LDS.128 and accumulates with packed FFMA2.  Slices are folded
+// through shared memory at the end.  Compared with the one-warp-per-group mapping this needs
+// ~3.5x fewer instructions per byte gathered and shortens an anchor's serial chain by `slices`.
+struct SmemLayout2 {
+  uint32_t w, loc, off, bw, widx, list, tab, red, bar, total;
+};
+__host__ __device__ inline SmemLayout2 smem_layout2(int P, int K, int L, int G, int C, int slices,
+                                                    int tap_pad) {
+  SmemLayout2 s;
+  const uint32_t taps = align_up(static_cast<uint32_t>(P) * K * L, tap_pad) + tap_pad;
+  uint32_t o = 0;
+  s.w = o, o = align_up(o + 4u * P * K * L * G, 16);
+  s.loc = o, o = align_up(o + 8u * P * K, 16);
+  s.off = o, o = align_up(o + 16u * taps, 16);
+  s.bw = o, o = align_up(o + 16u * taps, 16);
+  s.widx = o, o = align_up(o + 4u * taps, 16);
+  s.list = o, o = align_up(o + 4u * P * K, 16);
+  s.tab = o, o = align_up(o + 12u * K * L, 16);
+  s.red = o, o = align_up(o + 4u * slices * C, 16);
+  s.bar = o, o += 32;
+  s.total = o;
+  return s;
+}
+
+template <typename T, int U, bool TMA, int NT, int MINB, bool PF>
+__global__ void __launch_bounds__(NT, MINB)
+    dfa_fwd_rows_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                        const int *__restrict__ start, const float *__restrict__ loc,
+                        const float *__restrict__ weights, float *__restrict__ out, Dims d,
+                        int vpr_log2) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int vpr = 1 << vpr_log2;
+  const int slices = NT >> vpr_log2;
+  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  uint4 *s_off = reinterpret_cast<uint4 *>(smem + lay.off);
+  float4 *s_bw = reinterpret_cast<float4 *>(smem + lay.bw);
+  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  int *s_list = reinterpret_cast<int *>(smem + lay.list);
+  int *s_tab = reinterpret_cast<int *>(smem + lay.tab);
+  float *s_red = reinterpret_cast<float *>(smem + lay.red);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+
+  const int tid = threadIdx.x;
+  const int anchor = blockIdx.x;  // b * A + a
+  const int b = anchor / d.A;
+  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
+
+  // level tables → shared memory while the TMA copies are in flight
+  for (int i = tid; i < d.K * d.L; i += NT) {
+    s_tab[3 * i] = __ldg(shape + 2 * i);
+    s_tab[3 * i + 1] = __ldg(shape + 2 * i + 1);
+    s_tab[3 * i + 2] = __ldg(start + i);
+  }
+  const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
+                                        weights + static_cast<size_t>(anchor) * wcount, s_w,
+                                        s_loc, s_list, bars, s_nvalid, PK, wcount);
+  const int ntaps = nv * d.L;
+  const int step = slices * U;
+  const int ntaps_pad = (ntaps + step - 1) / step * step;
+
+  // Tap records.  Corner offsets are BYTE offsets inside the batch item.  A corner that falls
+  // outside the map (zero padding) is redirected to an in-bounds corner of the same tap with a
+  // zero bilinear weight — a valid sample always has one — so the main loop needs no predicates
+  // (and a non-finite feature there would reach the reference's result through the in-bounds
+  // corner as well).  Padding taps replay tap 0 with zero weights.
+  for (int t = tid; t < ntaps_pad; t += NT) {
+    const int tt = t < ntaps ? t : 0;
+    const int l = tt / nv, i = tt - l * nv;  // level-major: coarse-level neighbours back to back
+    const int s = s_list[i];
+    const int kl = (s % d.K) * d.L + l;
+    TapGeom gm;
+    tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], s_tab[3 * kl], s_tab[3 * kl + 1], s_tab[3 * kl + 2],
+                 gm);
+    const int safe = gm.row[0] >= 0 ? gm.row[0] : gm.row[1] >= 0 ? gm.row[1]
+                   : gm.row[2] >= 0 ? gm.row[2] : gm.row[3];
+    const float live = t < ntaps ? 1.f : 0.f;
+    const uint32_t rb = static_cast<uint32_t>(d.C) * sizeof(T);
+    uint4 off;
+    float4 bw;
+    off.x = (gm.row[0] >= 0 ? gm.row[0] : safe) * rb, bw.x = gm.row[0] >= 0 ? live * gm.hh * gm.hw : 0.f;
+    off.y = (gm.row[1] >= 0 ? gm.row[1] : safe) * rb, bw.y = gm.row[1] >= 0 ? live * gm.hh * gm.lw : 0.f;
+    off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, bw.z = gm.row[2] >= 0 ? live * gm.lh * gm.hw : 0.f;
+    off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, bw.w = gm.row[3] >= 0 ? live * gm.lh * gm.lw : 0.f;
+    s_off[t] = off, s_bw[t] = bw, s_widx[t] = (s * d.L + l) * d.G;
+    if (PF && t < ntaps) {
+      // start the rows' DRAM → L2 transfers now, long before the first register load needs them
+      const unsigned char *fr = reinterpret_cast<const unsigned char *>(feat) +
+                                static_cast<size_t>(b) * d.num_feat * rb;
+      if (gm.row[0] >= 0) tma_prefetch_l2(fr + off.x, rb);
+      if (gm.row[1] >= 0) tma_prefetch_l2(fr + off.y, rb);
+      if (gm.row[2] >= 0) tma_prefetch_l2(fr + off.z, rb);
+      if (gm.row[3] >= 0) tma_prefetch_l2(fr + off.w, rb);
+    }
+  }
+  __syncthreads();
+  if (TMA) mbar_wait(&bars[1], 0);  // weights have landed
+
+  const int slice = tid >> vpr_log2, v = tid & (vpr - 1);
+  const int ch = v * VEC;
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+
+  if (slice < slices) {
+    const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
+                              static_cast<size_t>(b) * d.num_feat * d.C * sizeof(T);
+    const uint32_t lane_off = static_cast<uint32_t>(ch) * sizeof(T);
+    const float *s_wg = s_w + ch / (d.C / d.G);
+    for (int t0 = slice; t0 < ntaps_pad; t0 += step) {
+      typename FeatVec<T>::raw_t val[U][4];
+      float cw[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + u * slices;
+        const uint4 off = s_off[t];
+        val[u][0] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.x + lane_off)));
+        val[u][1] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.y + lane_off)));
+        val[u][2] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.z + lane_off)));
+        val[u][3] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.w + lane_off)));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + u * slices;
+        const float4 bw = s_bw[t];
+        const float wgt = s_wg[s_widx[t]];
+        cw[u][0] = bw.x * wgt, cw[u][1] = bw.y * wgt, cw[u][2] = bw.z * wgt, cw[u][3] = bw.w * wgt;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) FeatVec<T>::fma(acc, cw[u][q], val[u][q]);
+    }
+    float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
+#pragma unroll
+    for (int c = 0; c < VEC / 4; ++c)
+      r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+  }
+  __syncthreads();
+  for (int c = tid; c < d.C; c += NT) {
+    float sum = 0.f;
+    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
+    out[static_cast<size_t>(anchor) * d.C + c] = sum;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// forward with row merging and a balanced gather (the default for SimPB's shapes)
+// ------------------------------------------------------------------------------------------
+// What bounds the gather on B200 is not HBM but the SM's load path — every 128 bytes a warp pulls
+// into registers is one L1 wavefront, hit or miss (ncu: l1tex data pipe 71 % busy on the
+// row-sliced kernel while DRAM sits at 34 %) — and, at one batch item, the length of each warp's
+// dependent chain.  So this kernel pulls fewer rows and keeps every warp's loads independent.
+// The key points of one anchor project close together: at the coarse levels their bilinear
+// corners name the same feature rows again and again (camera-rig inputs: 230 corner references
+// per anchor, 106 distinct rows).  They are merged without sorting or atomics:
+//
+//   prologue (warp 0)  the anchor's sampling locations arrive by one TMA bulk copy; the warp
+//                      compacts the samples that pass the op's (0,1) test and issues the weights
+//                      as TMA bulk copies too — one 128-byte line per VALID sample when the anchor
+//                      is sparse (a sample's L*G weights are contiguous), the whole block when it
+//                      is dense or when the grid is so small that latency, not bandwidth, rules.
+//   merge              warp l owns level l.  A chunk = up to 8 valid samples = 32 corner references,
+//                      one per lane.  __match_any_sync groups lanes that name the same row; the
+//                      lowest lane of each group sums the group's (bilinear weight x group weight)
+//                      coefficients with shuffles in ascending lane order.  Across the chunks of
+//                      the level a small direct-mapped table (row -> slot) in shared memory lets a
+//                      leader find a row an earlier chunk already listed and add to its
+//                      coefficients instead.  Result: a list of (row offset, coef[G]) per warp.
+//   gather             after one barrier every warp takes the same share of every list (slot p of
+//                      list c goes to warp (p + c) mod NW), so the warps finish together.  A lane
+//                      owns VPL 16-byte vectors of a row: one warp instruction covers 512 contiguous
+//                      bytes, U rows are in flight per lane, and the weighted sum stays in
+//                      registers (packed FFMA2).
+//   epilogue           the warps' partial rows are folded through shared memory and the anchor's
+//                      output row is written once.
+//
+// Merge and summation order are fixed, so results are bitwise reproducible.
+#ifdef DFA_PHASE_TIMING
+// Tool-only build (tools/phase_timing.py): per-warp clock64() stamps at the phase boundaries of the
+// merging forward kernel, written to a caller-provided buffer [anchor][warp][8].
+__device__ long long *g_phase_buf = nullptr;
+#define DFA_STAMP(i)                                                                      \
+  do {                                                                                    \
+    if (g_phase_buf && lane == 0)                                                         \
+      g_phase_buf[(static_cast<size_t>(blockIdx.x) * NW + warp) * 8 + (i)] = clock64();   \
+  } while (0)
+#else
+#define DFA_STAMP(i) do {} while (0)
+#endif
+
+// NW: warps per CTA.  U: rows in flight per lane.
+template <typename T, int VPL, int G, int NW, int U, bool TMA, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+    dfa_fwd_merge_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                         const int *__restrict__ start, const float *__restrict__ loc,
+                         const float *__restrict__ weights, float *__restrict__ out, Dims d,
+                         MergeLayout lay, int whole_weights, int prefetch) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  constexpr int NT = NW * 32;
+  constexpr int GPV = G / VPL;  // groups covered by one 512-byte segment of the row
+  constexpr int C = 32 * VPL * VEC;
+  static_assert(G % 4 == 0 && G % VPL == 0 && (32 * VPL) % G == 0,
+                "a 16-byte vector must lie inside one group");
+  static_assert((NW & (NW - 1)) == 0 && NW >= 2 && NW <= 32, "warps per CTA: a power of two");
+  static_assert(MERGE_CAP * G >= C, "partial rows must fit the coefficient lists");
+  static_assert(U == 2 || U == 4, "row offsets / slots of a batch are read with one vector load");
+  extern __shared__ __align__(128) unsigned char smem[];
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  uint32_t *s_list = reinterpret_cast<uint32_t *>(smem + lay.list);
+  int4 *s_tab = reinterpret_cast<int4 *>(smem + lay.tab);
+  uint32_t *s_rowoff = reinterpret_cast<uint32_t *>(smem + lay.rowoff);
+  float *s_coef = reinterpret_cast<float *>(smem + lay.coef);
+  int *s_cnt = reinterpret_cast<int *>(smem + lay.cnt);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int anchor = blockIdx.x;  // b * A + a
+  const int b = anchor / d.A;
+  const int PK = d.P * d.K, LG = d.L * G, wcount = PK * LG;
+  const float *loc_g = loc + static_cast<size_t>(anchor) * PK * 2;
+  const float *w_g = weights + static_cast<size_t>(anchor) * wcount;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  // ---- prologue ------------------------------------------------------------------------------
+  DFA_STAMP(0);
+  if (TMA) {
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&bars[0], 8u * PK);
+        tma_bulk_g2s(s_loc, loc_g, 8u * PK, &bars[0]);
+        if (whole_weights) {
+          mbar_expect_tx(&bars[1], 4u * wcount);
+          tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
+        }
+      }
+      __syncwarp();
+      if (NW == 1)
+        for (int i = lane; i < d.K * d.L; i += 32)
+          s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
+      mbar_wait(&bars[0], 0);
+    } else {
+      for (int i = tid - 32; i < d.K * d.L; i += NT - 32)
+        s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
+    }
+  } else {
+    for (int i = tid; i < 2 * PK; i += NT) s_loc[i] = __ldg(loc_g + i);
+    for (int i = tid; i < d.K * d.L; i += NT)
+      s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
+    __syncthreads();
+  }
+  DFA_STAMP(1);
+  bool sparse_w = false;  // weight lines packed by valid-sample index (stride LG + MERGE_WPAD)
+  if (warp == 0) {
+    // compaction: entry = sample | camera << 16, in sample order
+    const float rK = 1.0f / static_cast<float>(d.K);
+    int n = 0;
+    for (int base = 0; base < PK; base += 32) {
+      const int s = base + lane;
+      bool v = false;
+      if (s < PK) {
+        const float2 xy = *reinterpret_cast<const float2 *>(s_loc + 2 * s);
+        v = sample_valid(xy.x, xy.y);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, v);
+      if (v) {
+        const int p = static_cast<int>((static_cast<float>(s) + 0.5f) * rK);  // exact: s < 65536
+        s_list[n + __popc(m & lt_mask)] = static_cast<uint32_t>(s) | (static_cast<uint32_t>(s - p * d.K) << 16);
+      }
+      n += __popc(m);
+    }
+    sparse_w = TMA && !whole_weights && 2 * n <= PK;
+    if (lane == 0) *s_nvalid = sparse_w ? -n - 1 : n;
+    if (TMA && !whole_weights && n > 0) {
+      if (!sparse_w) {  // dense anchor: one copy of the whole block
+        if (lane == 0) {
+          mbar_expect_tx(&bars[1], 4u * wcount);
+          tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
+        }
+      } else {  // sparse anchor: one line per valid sample, packed by valid index
+        if (lane == 0) mbar_expect_tx(&bars[1], 4u * LG * n);
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+          const int s = s_list[i] & 0xffff;
+          tma_bulk_g2s(s_w + i * (LG + MERGE_WPAD), w_g + s * LG, 4u * LG, &bars[1]);
+        }
+      }
+    }
+  }
+  DFA_STAMP(2);
+  __syncthreads();
+  DFA_STAMP(3);
+  int nv = *s_nvalid;
+  sparse_w = nv < 0;
+  nv = sparse_w ? -nv - 1 : nv;
+  if (!TMA) {  // plain staging of the valid samples' weight lines
+    for (int i = tid; i < nv * LG; i += NT) {
+      const int s = s_list[i / LG] & 0xffff, r = i - (i / LG) * LG;
+      s_w[s * LG + r] = __ldg(w_g + s * LG + r);
+    }
+    __syncthreads();
+  }
+  const int wstride = sparse_w ? LG + MERGE_WPAD : LG;
+
+  const uint32_t rb = 512u * VPL;  // bytes per feature row
+  const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
+                            static_cast<size_t>(b) * d.num_feat * rb + lane * 16;
+  const int gq = (lane * G) / (32 * VPL);  // this lane's group inside each 512-byte segment
+  float acc[VPL][VEC];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[v][c] = 0.f;
+
+  // A warp's work items: (level, chunk of 8 valid samples) for its levels l = warp, warp + NW, ...
+  const int cpl = (nv + 7) >> 3;  // chunks per level
+  const int my_levels = warp < d.L ? (d.L - warp + NW - 1) / NW : 0;
+  const int max_items = ((d.L + NW - 1) / NW) * cpl;  // warp 0 has the most
+  uint32_t *s_table = reinterpret_cast<uint32_t *>(smem + lay.table) + warp * MERGE_TABLE;
+  uint32_t *my_rowoff = s_rowoff + warp * MERGE_CAP;
+  float *my_coef = s_coef + warp * MERGE_CAP * G;
+  uint32_t *s_mine_off = reinterpret_cast<uint32_t *>(smem + lay.mine_off) + warp * lay.mine_stride;
+  uint16_t *s_mine_slot = reinterpret_cast<uint16_t *>(smem + lay.mine_slot) + warp * lay.mine_stride;
+  bool wready = !TMA;
+  int li = 0, cj = 0;  // this warp's next item: its li-th level, chunk cj
+
+  for (int it0 = 0; it0 < max_items; it0 += 2) {
+    // ---- merge: this warp's next two chunks -------------------------------------------------------
+    int cnt = 0;
+    if (li < my_levels) {
+#pragma unroll
+      for (int x = 0; x < MERGE_TABLE / 128; ++x)
+        reinterpret_cast<uint4 *>(s_table)[x * 32 + lane] =
+            make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+      __syncwarp();
+    }
+    for (int x = 0; x < 2 && li < my_levels; ++x) {
+      const int l = warp + li * NW;
+      const int i = (cj << 3) + (lane >> 2), q = lane & 3;
+      if (++cj == cpl) cj = 0, ++li;
+      const bool live = i < nv;
+      const int ii = live ? i : 0;
+      const uint32_t ent = s_list[ii];
+      const int s = ent & 0xffff, k = ent >> 16;
+      const int4 tab = s_tab[k * d.L + l];
+      const float2 xy = *reinterpret_cast<const float2 *>(s_loc + 2 * s);
+      TapGeom gm;
+      tap_geometry(xy.x, xy.y, tab.x, tab.y, tab.z, gm);
+      const int row = q == 0 ? gm.row[0] : q == 1 ? gm.row[1] : q == 2 ? gm.row[2] : gm.row[3];
+      const float bw = ((q & 2) ? gm.lh : gm.hh) * ((q & 1) ? gm.lw : gm.hw);
+      const bool use = live && row >= 0;
+      const unsigned key = use ? static_cast<unsigned>(row) : (0x80000000u | lane);
+      const unsigned grp = __match_any_sync(0xffffffffu, key);
+      const bool leader = use && (static_cast<int>(__ffs(grp)) - 1 == lane);
+      if (!wready) {
+        mbar_wait(&bars[1], 0);  // weights have landed
+        wready = true;
+      }
+      // coefficients in the permuted order the gather reads them: [gq][v]  (g = v * GPV + gq)
+      float cf[G];
+      {
+        const float4 *wp = reinterpret_cast<const float4 *>(s_w + (sparse_w ? ii : s) * wstride + l * G);
+        float wv[G];
+#pragma unroll
+        for (int x = 0; x < G / 4; ++x) {
+          const float4 t = wp[x];
+          wv[4 * x] = t.x, wv[4 * x + 1] = t.y, wv[4 * x + 2] = t.z, wv[4 * x + 3] = t.w;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) cf[(g % GPV) * VPL + g / GPV] = use ? bw * wv[g] : 0.f;
+      }
+      // leaders add the coefficients of the other lanes of their group, lowest lane first
+      unsigned rem = leader ? (grp & ~(1u << lane)) : 0u;
+      const int n_it = __reduce_max_sync(0xffffffffu, __popc(rem));
+      for (int it = 0; it < n_it; ++it) {
+        const int src = rem ? (static_cast<int>(__ffs(rem)) - 1) : lane;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float v = __shfl_sync(0xffffffffu, cf[g], src);
+          if (rem) cf[g] += v;
+        }
+        rem &= rem - 1;
+      }
+      // has an earlier chunk of this round listed the row already?
+      const uint32_t h = (static_cast<uint32_t>(row) * 0x9E3779B1u) >> 25;  // MERGE_TABLE = 128
+      const uint32_t e = leader ? s_table[h] : 0xffffffffu;
+      const bool hit = leader && (e >> 6) == static_cast<uint32_t>(row);
+      const bool fresh = leader && !hit;
+      const unsigned fresh_m = __ballot_sync(0xffffffffu, fresh);
+      const int slot = hit ? static_cast<int>(e & 63u) : cnt + __popc(fresh_m & lt_mask);
+      float4 *cp = reinterpret_cast<float4 *>(my_coef + slot * G);
+      if (hit) {
+#pragma unroll
+        for (int x = 0; x < G / 4; ++x) {
+          float4 t = cp[x];
+          t.x += cf[4 * x], t.y += cf[4 * x + 1], t.z += cf[4 * x + 2], t.w += cf[4 * x + 3];
+          cp[x] = t;
+        }
+      } else if (fresh) {
+        s_table[h] = (static_cast<uint32_t>(row) << 6) | static_cast<uint32_t>(slot);
+        my_rowoff[slot] = static_cast<uint32_t>(row) * rb;
+        if (prefetch == 1)  // start the row's DRAM -> L2 transfer now; the gather then runs at L2 latency
+          tma_prefetch_l2(fb - lane * 16 + static_cast<uint32_t>(row) * rb, rb);
+        else if (prefetch == 2)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(fb - lane * 16 + static_cast<uint32_t>(row) * rb));
+#pragma unroll
+        for (int x = 0; x < G / 4; ++x)
+          cp[x] = make_float4(cf[4 * x], cf[4 * x + 1], cf[4 * x + 2], cf[4 * x + 3]);
+      }
+      cnt += __popc(fresh_m);
+      __syncwarp();
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
+    DFA_STAMP(4);
+    __syncthreads();
+    DFA_STAMP(5);
+    // ---- this warp's share: slot p of list c goes to warp (p + c) mod NW --------------------------
+    int n_mine = 0;
+#pragma unroll
+    for (int c = 0; c < NW; ++c) {
+      const int cn = s_cnt[c];
+      const int first = (warp - c) & (NW - 1);
+      const int mine = cn > first ? (cn - first + NW - 1) / NW : 0;
+      if (lane < mine) {
+        const int slot = c * MERGE_CAP + first + lane * NW;
+        s_mine_off[n_mine + lane] = s_rowoff[slot];
+        s_mine_slot[n_mine + lane] = static_cast<uint16_t>(slot);
+      }
+      n_mine += mine;
+    }
+    if (lane < U) {  // padding up to a multiple of U: no load, zero coefficients
+      s_mine_off[n_mine + lane] = 0xffffffffu;
+      s_mine_slot[n_mine + lane] = 0;
+    }
+    __syncwarp();
+    // ---- gather: every distinct row once ----------------------------------------------------------
+    for (int k0 = 0; k0 < n_mine; k0 += U) {
+      typename FeatVec<T>::raw_t val[U][VPL];
+      uint32_t off[U];
+      int slot[U];
+      if constexpr (U == 4) {
+        const uint4 o4 = *reinterpret_cast<const uint4 *>(s_mine_off + k0);
+        const uint2 s2 = *reinterpret_cast<const uint2 *>(s_mine_slot + k0);
+        off[0] = o4.x, off[1] = o4.y, off[2] = o4.z, off[3] = o4.w;
+        slot[0] = s2.x & 0xffff, slot[1] = s2.x >> 16, slot[2] = s2.y & 0xffff, slot[3] = s2.y >> 16;
+      } else {
+        const uint2 o2 = *reinterpret_cast<const uint2 *>(s_mine_off + k0);
+        const uint32_t s1 = *reinterpret_cast<const uint32_t *>(s_mine_slot + k0);
+        off[0] = o2.x, off[1] = o2.y;
+        slot[0] = s1 & 0xffff, slot[1] = s1 >> 16;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = off[u] != 0xffffffffu;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+          val[u][v] = ok ? FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off[u] + 512u * v)))
+                         : FeatVec<T>::zero_raw();
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = off[u] != 0xffffffffu;
+        const float *cp = s_coef + slot[u] * G + gq * VPL;
+        float cv[VPL];
+        if (VPL == 2) {
+          const float2 t = *reinterpret_cast<const float2 *>(cp);
+          cv[0] = ok ? t.x : 0.f, cv[VPL - 1] = ok ? t.y : 0.f;
+        } else {
+          cv[0] = ok ? *cp : 0.f;
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) FeatVec<T>::fma(acc[v], cv[v], val[u][v]);
+      }
+    }
+    DFA_STAMP(6);
+    __syncthreads();  // the lists are free again (next round, or the partial rows)
+  }
+  if (TMA && whole_weights && !wready) mbar_wait(&bars[1], 0);  // never exit with a copy in flight
+
+  // ---- epilogue: fold the warps' partial rows ---------------------------------------------------
+  {
+    float *part = s_coef + warp * C;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      float4 *o = reinterpret_cast<float4 *>(part + (v * 32 + lane) * VEC);
+#pragma unroll
+      for (int c = 0; c < VEC / 4; ++c)
+        o[c] = make_float4(acc[v][4 * c], acc[v][4 * c + 1], acc[v][4 * c + 2], acc[v][4 * c + 3]);
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += NT) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sum += s_coef[w * C + c];
+    out[static_cast<size_t>(anchor) * C + c] = sum;
+  }
+  DFA_STAMP(7);
+}
+
+// Shape-generic forward (any C, G with C % G == 0, any alignment): one CTA per anchor, threads
+// stride over channels, scalar loads.  Same staging/geometry code, no atomics.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    dfa_fwd_generic_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                           const int *__restrict__ start, const float *__restrict__ loc,
+                           const float *__restrict__ weights, float *__restrict__ out, Dims d) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, 1, false);
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  TapQ *s_rec = reinterpret_cast<TapQ *>(smem + lay.rec);
+  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  int *s_list = reinterpret_cast<int *>(smem + lay.list);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
+  const int tid = threadIdx.x, anchor = blockIdx.x, b = anchor / d.A;
+  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
+  const int nv = stage_and_compact<false>(loc + static_cast<size_t>(anchor) * PK * 2,
+                                          weights + static_cast<size_t>(anchor) * wcount, s_w,
+                                          s_loc, s_list, bars, s_nvalid, PK, wcount);
+  const int ntaps = nv * d.L;
+  for (int t = tid; t < ntaps; t += blockDim.x) {
+    const int l = t / nv, i = t - l * nv, s = s_list[i], k = s % d.K, kl = k * d.L + l;
+    const int H = __ldg(shape + 2 * kl), W = __ldg(shape + 2 * kl + 1);
+    TapGeom gm;
+    tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], H, W, __ldg(start + kl), gm);
+    const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
+    for (int q = 0; q < 4; ++q) {
+      s_rec[4 * t + q].off = gm.row[q] >= 0 ? gm.row[q] * d.C : -1;
+      s_rec[4 * t + q].bw = gm.row[q] >= 0 ? bw[q] : 0.f;
+    }
+    s_widx[t] = (s * d.L + l) * d.G;
+  }
+  __syncthreads();
+  const int cpg = d.C / d.G;
+  const T *fb = feat + static_cast<size_t>(b) * d.num_feat * d.C;
+  for (int c = tid; c < d.C; c += blockDim.x) {
+    const int grp = c / cpg;
+    float acc = 0.f;
+    for (int t = 0; t < ntaps; ++t) {
+      const float wgt = s_w[s_widx[t] + grp];
+      float val = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const TapQ r = s_rec[4 * t + q];
+        if (r.off >= 0) val = fmaf(r.bw, static_cast<float>(fb[r.off + c]), val);
+      }
+      acc = fmaf(wgt, val, acc);
+    }
+    out[static_cast<size_t>(anchor) * d.C + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// side channel for the bit-exact parity tests: the geometry above, nothing else
+// ------------------------------------------------------------------------------------------
+__global__ void dfa_debug_indices_kernel(const int *__restrict__ shape, const int *__restrict__ start,
+                                         const float *__restrict__ loc, uint8_t *__restrict__ valid,
+                                         int *__restrict__ rows, Dims d) {
+  const long long n = static_cast<long long>(d.bs) * d.A * d.P * d.K;
+  for (long long s = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; s < n;
+       s += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(s % d.K);
+    const float x = loc[2 * s], y = loc[2 * s + 1];
+    const bool ok = sample_valid(x, y);
+    valid[s] = ok ? 1 : 0;
+    for (int l = 0; l < d.L; ++l) {
+      const int kl = k * d.L + l;
+      TapGeom gm;
+      tap_geometry(x, y, shape[2 * kl], shape[2 * kl + 1], start[kl], gm);
+      for (int q = 0; q < 4; ++q) rows[(s * d.L + l) * 4 + q] = ok ? gm.row[q] : -1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers and dispatch
+// ------------------------------------------------------------------------------------------
+constexpr int FWD_U = 4;
+
+template <typename T, int LPG, bool TMA, int MAXT>
+int launch_fwd_t(const void *feat, const int *shape, const int *start, const float *loc,
+                 const float *w, float *out, const Dims &d, cudaStream_t st) {
+  auto kern = dfa_fwd_kernel<T, LPG, FWD_U, TMA, MAXT>;
+  constexpr int TPW = 32 / (4 * LPG);
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, TPW * FWD_U, false);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  kern<<<d.bs * d.A, 32 * d.G, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
+                                               out, d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+#define DFA_DISPATCH_LPG(CALL)                    \
+  switch (lpg) {                                  \
+    case 8: return CALL(8);                       \
+    case 4: return CALL(4);                       \
+    case 2: return CALL(2);                       \
+    default: return CALL(1);                      \
+  }
+
+template <typename T, int U, bool TMA, int NT, int MINB, bool PF>
+int launch_fwd_rows(const void *feat, const int *shape, const int *start, const float *loc,
+                    const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
+  auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB, PF>;
+  const int slices = NT / vpr;
+  int vpr_log2 = 0;
+  while ((1 << vpr_log2) < vpr) ++vpr_log2;
+  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  kern<<<d.bs * d.A, NT, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w, out, d,
+                                          vpr_log2);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Row-sliced fast path: the row is a power-of-two number of 16-byte vectors (<= block size) and
+// every vector lies inside one channel group.
+template <typename T>
+int rows_vpr(const Dims &d, const void *feat, int nt) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  if (d.C % VEC != 0 || (d.C / d.G) % VEC != 0 || !aligned(feat, 16)) return 0;
+  const int vpr = d.C / VEC;
+  if (vpr > nt || nt % vpr != 0 || (vpr & (vpr - 1)) != 0) return 0;
+  if (static_cast<long long>(d.num_feat) * d.C * static_cast<long long>(sizeof(T)) >= (1ll << 32)) return 0;
+  return vpr;
+}
+
+template <typename T, int VPL, int NW, int U, bool TMA, int MINB>
+int launch_fwd_merge(const void *feat, const int *shape, const int *start, const float *loc,
+                     const float *w, float *out, const Dims &d, cudaStream_t st) {
+  auto kern = dfa_fwd_merge_kernel<T, VPL, 8, NW, U, TMA, MINB>;
+  const MergeLayout lay = merge_layout(d.P, d.K, d.L, d.G, NW, U);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  // A grid that fits the machine in about one wave is bound by latency, not bandwidth: fetch the
+  // whole weights block at once instead of waiting for the sample mask first.
+  const long long grid = static_cast<long long>(d.bs) * d.A;
+  const int whole = env_int("DFA_FWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0);
+  const int prefetch = env_int("DFA_FWD_PREFETCH", 0);
+  kern<<<d.bs * d.A, NW * 32, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
+                                              out, d, lay, whole, prefetch);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T>
+int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
+                  const float *w, float *out, const Dims &d, cudaStream_t st) {
+  // DFA_FWD_VARIANT (tuning knob): 1..4 = row-sliced kernel with (threads, taps in flight) =
+  // (256,1) (256,2) (512,1) (512,2) — 1 is the default, the fastest measured on B200 at SimPB's
+  // shapes; 10.. = row-merging kernel (fewer DRAM bytes and L1 wavefronts, longer dependent chain
+  // per warp: within 5-25 % of the default); 0 = one-warp-per-group kernel.
+  // A variant whose shape constraints are not met falls through to the next family.
+  const int variant = env_int("DFA_FWD_VARIANT", 1);
+  if (variant >= 10) {  // merging kernel: (warps, rows in flight, CTAs per SM) per variant
+    const int vpl = merge_vpl<T>(d, feat);
+    if (vpl) {
+      const bool tma = warp_tma_ok(d, loc, w);
+#define WARPK(VPL, NW, U, MINB)                                                                  \
+  (tma ? launch_fwd_merge<T, VPL, NW, U, true, MINB>(feat, shape, start, loc, w, out, d, st)       \
+       : launch_fwd_merge<T, VPL, NW, U, false, MINB>(feat, shape, start, loc, w, out, d, st))
+#define WARPV(NW, U, MINB) (vpl == 2 ? WARPK(2, NW, U, MINB) : WARPK(1, NW, U, MINB))
+      switch (variant) {
+        case 11: return WARPV(4, 4, 8);
+        case 12: return WARPV(4, 4, 9);
+        case 13: return WARPV(4, 2, 12);
+        case 14: return WARPV(8, 4, 5);
+        case 15: return WARPV(8, 4, 4);
+        case 16: return WARPV(8, 2, 6);
+        case 17: return WARPV(2, 4, 18);
+        default: return WARPV(4, 4, 10);
+      }
+#undef WARPV
+#undef WARPK
+    }
+  }
+  const int rvariant = variant >= 10 ? 1 : variant;
+  if (rvariant >= 1) {
+    const int nt = rvariant == 5 ? 192 : rvariant == 6 ? 128 : rvariant >= 3 ? 512 : 256;
+    const int vpr = rows_vpr<T>(d, feat, nt);
+    if (vpr) {
+      const bool tma = tma_ok(d, loc, w);
+      const bool pf = env_int("DFA_FWD_PREFETCH", 0) != 0;
+#define ROWS(U, NT, MINB)                                                                              \
+  (tma ? (pf ? launch_fwd_rows<T, U, true, NT, MINB, true>(feat, shape, start, loc, w, out, d, vpr, st)  \
+             : launch_fwd_rows<T, U, true, NT, MINB, false>(feat, shape, start, loc, w, out, d, vpr, st)) \
+       : launch_fwd_rows<T, U, false, NT, MINB, false>(feat, shape, start, loc, w, out, d, vpr, st))
+      switch (rvariant) {
+        case 1: return ROWS(1, 256, 6);
+        case 2: return ROWS(2, 256, 4);
+        case 3: return ROWS(1, 512, 3);
+        case 5: return ROWS(1, 192, 8);
+        case 6: return ROWS(1, 128, 12);
+        default: return ROWS(2, 512, 2);
+      }
+#undef ROWS
+    }
+  }
+  const int lpg = fast_lpg<T>(d, feat);
+  if (lpg && aligned(out, 16)) {
+    const bool tma = tma_ok(d, loc, w);
+    const bool small = 32 * d.G <= 256;
+#define CALL_FWD(N)                                                                            \
+  (tma ? (small ? launch_fwd_t<T, N, true, 256>(feat, shape, start, loc, w, out, d, st)        \
+                : launch_fwd_t<T, N, true, 1024>(feat, shape, start, loc, w, out, d, st))      \
+       : (small ? launch_fwd_t<T, N, false, 256>(feat, shape, start, loc, w, out, d, st)       \
+                : launch_fwd_t<T, N, false, 1024>(feat, shape, start, loc, w, out, d, st)))
+    DFA_DISPATCH_LPG(CALL_FWD)
+#undef CALL_FWD
+  }
+  auto kern = dfa_fwd_generic_kernel<T>;
+  const SmemLayout lay = smem_layout(d.P, d.K, d.L, d.G, 1, false);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  const int threads = d.C >= 256 ? 256 : ((d.C + 31) / 32) * 32;
+  kern<<<d.bs * d.A, threads, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
+                                              out, d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" {
+
+int dfa_version(void) { return DFA_B200_VERSION; }
+
+#ifdef DFA_PHASE_TIMING
+int dfa_debug_set_phase_buffer(long long *buf) {
+  return static_cast<int>(cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf)));
+}
+#endif
+
+const char *dfa_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case DFA_ERR_NULL_POINTER: return "dfa: null pointer argument";
+    case DFA_ERR_BAD_DIMS: return "dfa: bad dimensions (non-positive, C % G != 0, or index overflow)";
+    case DFA_ERR_BAD_DTYPE: return "dfa: unsupported feature dtype";
+    case DFA_ERR_MISALIGNED: return "dfa: pointer not aligned for its element type";
+    case DFA_ERR_UNSUPPORTED: return "dfa: configuration not supported (shared memory budget)";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "dfa: unknown error";
+  }
+}
+
+int dfa_forward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_shape,
+                const int32_t *scale_start_index, const float *sampling_location,
+                const float *weights, float *output, const dfa_dims *dims, void *stream) {
+  if (!mc_ms_feat || !spatial_shape || !scale_start_index || !sampling_location || !weights || !output)
+    return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  if (!aligned(sampling_location, 4) || !aligned(weights, 4) || !aligned(output, 4) ||
+      !aligned(spatial_shape, 4) || !aligned(scale_start_index, 4))
+    return DFA_ERR_MISALIGNED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (feat_dtype == DFA_F32) {
+    if (!aligned(mc_ms_feat, 4)) return DFA_ERR_MISALIGNED;
+    return forward_typed<float>(mc_ms_feat, spatial_shape, scale_start_index, sampling_location,
+                                weights, output, d, st);
+  }
+  if (feat_dtype == DFA_BF16) {
+    if (!aligned(mc_ms_feat, 2)) return DFA_ERR_MISALIGNED;
+    return forward_typed<__nv_bfloat16>(mc_ms_feat, spatial_shape, scale_start_index,
+                                        sampling_location, weights, output, d, st);
+  }
+  return DFA_ERR_BAD_DTYPE;
+}
+
+int dfa_debug_indices(const int32_t *spatial_shape, const int32_t *scale_start_index,
+                      const float *sampling_location, uint8_t *valid, int32_t *corner_rows,
+                      const dfa_dims *dims, void *stream) {
+  if (!spatial_shape || !scale_start_index || !sampling_location || !valid || !corner_rows)
+    return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  const long long n = static_cast<long long>(d.bs) * d.A * d.P * d.K;
+  const int blocks = static_cast<int>((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  dfa_debug_indices_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      spatial_shape, scale_start_index, sampling_location, valid, corner_rows, d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int64_t dfa_forward_host_workspace_bytes(int feat_dtype, const dfa_dims *dims) {
+  Dims d;
+  if (check_dims(dims, d)) return -1;
+  const int64_t esz = feat_dtype == DFA_BF16 ? 2 : 4;
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  return up(esz * d.bs * d.num_feat * d.C) + up(8ll * d.K * d.L) + up(4ll * d.K * d.L) +
+         up(8ll * d.bs * d.A * d.P * d.K) + up(4ll * d.bs * d.A * d.P * d.K * d.L * d.G) +
+         up(4ll * d.bs * d.A * d.C);
+}
+
+int dfa_forward_host(const void *h_feat, int feat_dtype, const int32_t *h_shape,
+                     const int32_t *h_start, const float *h_loc, const float *h_w, float *h_out,
+                     const dfa_dims *dims, void *workspace, int64_t workspace_bytes, void *stream) {
+  if (!h_feat || !h_shape || !h_start || !h_loc || !h_w || !h_out || !workspace)
+    return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  if (feat_dtype != DFA_F32 && feat_dtype != DFA_BF16) return DFA_ERR_BAD_DTYPE;
+  if (workspace_bytes < dfa_forward_host_workspace_bytes(feat_dtype, dims)) return DFA_ERR_BAD_DIMS;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t esz = feat_dtype == DFA_BF16 ? 2 : 4;
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  char *p = static_cast<char *>(workspace);
+  const int64_t nb_feat = esz * d.bs * d.num_feat * d.C, nb_shape = 8ll * d.K * d.L,
+                nb_start = 4ll * d.K * d.L, nb_loc = 8ll * d.bs * d.A * d.P * d.K,
+                nb_w = 4ll * d.bs * d.A * d.P * d.K * d.L * d.G, nb_out = 4ll * d.bs * d.A * d.C;
+  void *d_feat = p; p += up(nb_feat);
+  int32_t *d_shape = reinterpret_cast<int32_t *>(p); p += up(nb_shape);
+  int32_t *d_start = reinterpret_cast<int32_t *>(p); p += up(nb_start);
+  float *d_loc = reinterpret_cast<float *>(p); p += up(nb_loc);
+  float *d_w = reinterpret_cast<float *>(p); p += up(nb_w);
+  float *d_out = reinterpret_cast<float *>(p);
+  cudaError_t e;
+  // small operands first so the kernel's staging data is resident before the big copy ends
+  if ((e = cudaMemcpyAsync(d_shape, h_shape, nb_shape, cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemcpyAsync(d_start, h_start, nb_start, cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemcpyAsync(d_loc, h_loc, nb_loc, cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemcpyAsync(d_w, h_w, nb_w, cudaMemcpyHostToDevice, st))) return e;
+  if ((e = cudaMemcpyAsync(d_feat, h_feat, nb_feat, cudaMemcpyHostToDevice, st))) return e;
+  if (int rc = dfa_forward(d_feat, feat_dtype, d_shape, d_start, d_loc, d_w, d_out, dims, stream))
+    return rc;
+  if ((e = cudaMemcpyAsync(h_out, d_out, nb_out, cudaMemcpyDeviceToHost, st))) return e;
+  return static_cast<int>(cudaStreamSynchronize(st));
+}
+
+}  // extern "C"

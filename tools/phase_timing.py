@@ -23,8 +23,9 @@ a = ap.parse_args()
 os.environ["DFA_FWD_VARIANT"] = str(a.variant)
 lib_path = os.path.join(ROOT, "gpurun_out", "libdfa_b200_prof.so")
 os.makedirs(os.path.dirname(lib_path), exist_ok=True)
-subprocess.check_call(["nvcc"] + build.NVCC_FLAGS + ["-DDFA_PHASE_TIMING", "-I", os.path.join(ROOT, "include"),
-                                                    "-o", lib_path, build.KERNEL_SRC])
+objs, _ = build.compile_objects(extra_flags=["-DDFA_PHASE_TIMING"],
+                                obj_dir=os.path.join(ROOT, "gpurun_out", "prof_objs"))
+build.link_lib(objs, lib_path)
 lib = ctypes.CDLL(lib_path)
 
 

@@ -10,9 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from simpb_b200 import build  # noqa: E402
 
-cmd = ["nvcc"] + build.NVCC_FLAGS + ["-Xptxas=-v", "-I", os.path.join(ROOT, "include"), "-o", build.LIB,
-                                     build.KERNEL_SRC]
-err = subprocess.run(cmd, capture_output=True, text=True).stderr
+_, err = build.compile_objects(verbose=True, obj_dir="/tmp/dfa_ptxas_report")
 filt = sys.argv[1] if len(sys.argv) > 1 else ""
 name = None
 for line in err.splitlines():
