@@ -22,6 +22,8 @@
  *   dfa_softmax_weights_backward     autograd of the above
  *   dfa_softmax_weights_split(_backward)  the same for models/blocks.py:166-174's camera-embedding
  *                          branch, with the broadcast add folded into the kernel
+ *   dfa_msda_forward / _backward     mmcv-full 1.7.1 MultiScaleDeformableAttnFunction as called at
+ *                          models/group_attn.py:229-233 (third-party kernel, not vendored)
  *   dfa_forward_host       the same forward, called with HOST buffers (copies inside)
  *
  * Tensor layouts (row-major, innermost last) — ops/src/deformable_aggregation.cpp:22-28:
@@ -150,6 +152,25 @@ int dfa_softmax_weights_split_backward(const float *logits_anchor, const float *
                                        float *grad_logits_anchor, int bs, int num_anchors,
                                        int num_cams, int num_scale, int num_pts, int num_groups,
                                        void *stream);
+
+/* Multi-scale deformable attention of the 2-D query branch — replaces mmcv-full 1.7.1's
+ * MultiScaleDeformableAttnFunction (ms_deform_attn_forward / _backward) at the reference call site
+ * models/group_attn.py:229-233.  value [bs, S, M, D] (float32 or bfloat16; for SimPB a view of one
+ * camera's slice of the mc_ms_feat table), spatial_shapes [L,2] (H,W), level_start_index [L],
+ * sampling_loc [bs,Q,M,L,P,2] (x,y), attn_weight [bs,Q,M,L,P] → output [bs,Q,M*D] float32, written
+ * (no zero-fill needed).  Backward: grad_sampling_loc and grad_attn_weight are fully written;
+ * grad_value [bs,S,M,D] float32 is accumulated into (zero_grad_value != 0: zero-filled on the stream
+ * first; NULL: skipped). */
+int dfa_msda_forward(const void *value, int value_dtype, const int32_t *spatial_shapes,
+                     const int32_t *level_start_index, const float *sampling_loc,
+                     const float *attn_weight, float *output, int bs, int num_value, int num_heads,
+                     int head_dim, int num_query, int num_levels, int num_points, void *stream);
+int dfa_msda_backward(const void *value, int value_dtype, const int32_t *spatial_shapes,
+                      const int32_t *level_start_index, const float *sampling_loc,
+                      const float *attn_weight, const float *grad_output, float *grad_value,
+                      float *grad_sampling_loc, float *grad_attn_weight, int bs, int num_value,
+                      int num_heads, int head_dim, int num_query, int num_levels, int num_points,
+                      int zero_grad_value, void *stream);
 
 /* Forward with HOST buffers: host→device copies of all five inputs, the kernel, and the
  * device→host copy of the output, on `stream`, then a stream synchronise.  Host buffers should

@@ -1,6 +1,6 @@
 """In-tree build of the native code (sm_100a only).
 
-  libdfa_b200.so                          CUDA kernels + the C ABI of include/dfa_b200.h (nvcc; three
+  libdfa_b200.so                          CUDA kernels + the C ABI of include/dfa_b200.h (nvcc; four
                                           translation units under csrc/, compiled in parallel)
   ops/deformable_aggregation_ext*.so      thin torch extension with the reference's two entry
                                           points, forwarding raw pointers to the C ABI (g++)
@@ -15,7 +15,8 @@ import sysconfig
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, "libdfa_b200.so")
-KERNEL_SRCS = [os.path.join(PKG, "csrc", n) for n in ("dfa_forward.cu", "dfa_backward.cu", "dfa_frontend.cu")]
+KERNEL_SRCS = [os.path.join(PKG, "csrc", n) for n in ("dfa_forward.cu", "dfa_backward.cu", "dfa_frontend.cu",
+                                                        "dfa_msda.cu")]
 COMMON_HDR = os.path.join(PKG, "csrc", "dfa_common.cuh")
 OBJ_DIR = os.path.join(PKG, "csrc", "build")
 EXT_SRC = os.path.join(PKG, "csrc", "dfa_torch_ext.cpp")

@@ -20,6 +20,7 @@ SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_forward", "dfa_backward", "df
            "dfa_flatten_maps", "dfa_keypoints_project", "dfa_keypoints_project_backward",
            "dfa_softmax_weights", "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
            "dfa_softmax_weights_split_backward",
+           "dfa_msda_forward", "dfa_msda_backward",
            "dfa_forward_host_workspace_bytes", "dfa_forward_host")
 
 
@@ -55,13 +56,17 @@ def _load():
     lib.dfa_softmax_weights_split.argtypes = [vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.dfa_softmax_weights_split_backward.argtypes = [vp, vp, vp, f32, vp, vp, vp, i32, i32, i32, i32,
                                                        i32, i32, vp]
+    lib.dfa_msda_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.dfa_msda_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                      i32, i32, i32, vp]
     lib.dfa_forward_host_workspace_bytes.restype = i64
     lib.dfa_forward_host_workspace_bytes.argtypes = [i32, dp]
     lib.dfa_forward_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp, i64, vp]
     for name in ("dfa_forward", "dfa_backward", "dfa_debug_indices", "dfa_flatten_maps",
                  "dfa_keypoints_project", "dfa_keypoints_project_backward", "dfa_softmax_weights",
                  "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
-                 "dfa_softmax_weights_split_backward", "dfa_forward_host"):
+                 "dfa_softmax_weights_split_backward", "dfa_msda_forward", "dfa_msda_backward",
+                 "dfa_forward_host"):
         getattr(lib, name).restype = i32
     return lib
 
@@ -344,6 +349,52 @@ def softmax_weights_split_backward(logits_anchor, logits_cam, dims, keep, scale,
             float(scale), grad_w.data_ptr(), g_full.data_ptr(), g_anchor.data_ptr(), bs, A, K, L, P, G,
             stream_ptr(grad_w.device)), "dfa_softmax_weights_split_backward")
     return g_anchor, g_full.sum(dim=1).reshape(logits_cam.shape)
+
+
+def _msda_dims(value, shapes, start, loc, w):
+    _need(value, "value"); _need(shapes, "spatial_shapes", torch.int32)
+    _need(start, "level_start_index", torch.int32)
+    _need(loc, "sampling_locations", torch.float32); _need(w, "attention_weights", torch.float32)
+    if value.dim() != 4 or loc.dim() != 6 or loc.shape[5] != 2 or w.dim() != 5 or shapes.dim() != 2:
+        raise DfaError("msda: value [bs,S,M,D], loc [bs,Q,M,L,P,2], weights [bs,Q,M,L,P] expected")
+    bs, S, M, D = value.shape
+    Q, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+    if tuple(loc.shape) != (bs, Q, M, L, P, 2) or tuple(w.shape) != (bs, Q, M, L, P) \
+            or tuple(shapes.shape) != (L, 2) or start.numel() != L:
+        raise DfaError("msda: inconsistent shapes value=%s loc=%s weights=%s shapes=%s"
+                       % (tuple(value.shape), tuple(loc.shape), tuple(w.shape), tuple(shapes.shape)))
+    return bs, S, M, D, Q, L, P
+
+
+def msda_forward(value, shapes, start, loc, w):
+    bs, S, M, D, Q, L, P = _msda_dims(value, shapes, start, loc, w)
+    out = torch.empty(bs, Q, M * D, device=value.device, dtype=torch.float32)
+    if bs == 0 or Q == 0:
+        return out
+    with torch.cuda.device(value.device):
+        check(lib.dfa_msda_forward(value.data_ptr(), feat_dtype(value), shapes.data_ptr(), start.data_ptr(),
+                                   loc.data_ptr(), w.data_ptr(), out.data_ptr(), bs, S, M, D, Q, L, P,
+                                   stream_ptr(value.device)), "dfa_msda_forward")
+    return out
+
+
+def msda_backward(value, shapes, start, loc, w, grad_out, need_value=True):
+    bs, S, M, D, Q, L, P = _msda_dims(value, shapes, start, loc, w)
+    _need(grad_out, "grad_output", torch.float32)
+    if grad_out.numel() != bs * Q * M * D:
+        raise DfaError("msda: grad_output must be [bs, Q, M*D]")
+    gv = torch.empty(value.shape, device=value.device, dtype=torch.float32) if need_value else None
+    gl, gw = torch.empty_like(loc), torch.empty_like(w)
+    if bs == 0 or Q == 0:
+        if gv is not None:
+            gv.zero_()
+        return gv, gl, gw
+    with torch.cuda.device(value.device):
+        check(lib.dfa_msda_backward(value.data_ptr(), feat_dtype(value), shapes.data_ptr(), start.data_ptr(),
+                                    loc.data_ptr(), w.data_ptr(), grad_out.data_ptr(),
+                                    gv.data_ptr() if gv is not None else None, gl.data_ptr(), gw.data_ptr(),
+                                    bs, S, M, D, Q, L, P, 1, stream_ptr(value.device)), "dfa_msda_backward")
+    return gv, gl, gw
 
 
 class HostForward:

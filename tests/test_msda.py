@@ -1,0 +1,178 @@
+"""Multi-scale deformable attention (the 2-D query branch's gather).  mmcv-full 1.7.1 is not
+vendored, so there are no reference vectors: the C oracle (mmcv's CUDA kernel restated) and the
+grid_sample formulation (mmcv's CPU fallback restated) are first checked against each other, then
+the CUDA kernels against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import msda_ref
+from helpers import RTOL_BF16, RTOL_F32, assert_close
+
+SIZES3 = ((8, 12), (4, 6), (2, 3))
+
+
+def make_case(seed, bs, Q, M, D, sizes, P, lo=-0.15, hi=1.15):
+    g = torch.Generator().manual_seed(seed)
+    shapes = torch.tensor(sizes, dtype=torch.int64)
+    counts = shapes[:, 0] * shapes[:, 1]
+    start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]])
+    S, L = int(counts.sum()), len(sizes)
+    return dict(value=torch.randn(bs, S, M, D, generator=g), shapes=shapes, start=start,
+                loc=torch.rand(bs, Q, M, L, P, 2, generator=g) * (hi - lo) + lo,
+                w=torch.rand(bs, Q, M, L, P, generator=g).reshape(bs, Q, M, -1).softmax(-1)
+                .reshape(bs, Q, M, L, P),
+                go=torch.randn(bs, Q, M * D, generator=g))
+
+
+# ------------------------------------------------------------------ CPU: the two oracles agree
+@pytest.mark.parametrize("cfg", [dict(bs=2, Q=7, M=4, D=8, sizes=SIZES3, P=4),
+                                 dict(bs=1, Q=5, M=8, D=32, sizes=SIZES3, P=4),
+                                 dict(bs=1, Q=3, M=2, D=5, sizes=((5, 7),), P=3)])
+def test_c_oracle_matches_grid_sample_formulation(cfg):
+    d = make_case(1, **cfg)
+    out = msda_ref.forward(d["value"], d["shapes"], d["start"], d["loc"], d["w"])
+    v, l, w = (d[k].double().requires_grad_() for k in ("value", "loc", "w"))
+    ref = msda_ref.msda_grid_sample(v, d["shapes"], l, w)
+    assert_close(out, ref, 2e-6, "forward")
+    ref.backward(d["go"].double())
+    gv, gl, gw = msda_ref.backward(d["value"], d["shapes"], d["start"], d["loc"], d["w"], d["go"])
+    assert_close(gv, v.grad, 2e-6, "grad_value")
+    assert_close(gw, w.grad, 2e-6, "grad_attn_weight")
+    assert_close(gl, l.grad, 1e-5, "grad_sampling_loc")
+
+
+def test_taps_outside_the_border_band_contribute_nothing():
+    """h_im > -1 && w_im > -1 && h_im < H && w_im < W: one pixel beyond the map is the limit."""
+    d = make_case(2, bs=1, Q=2, M=1, D=4, sizes=((4, 4),), P=2)
+    d["loc"][0, 0, 0, 0, 0] = torch.tensor([-0.13, 0.5])       # w_im = -1.02: not taken
+    d["loc"][0, 0, 0, 0, 1] = torch.tensor([-0.12, 0.5])       # w_im = -0.98: taken, weight on column 0 only
+    d["loc"][0, 1, 0, 0, 0] = torch.tensor([0.5, 1.13])        # h_im = 4.02: not taken
+    d["loc"][0, 1, 0, 0, 1] = torch.tensor([0.5, 1.12])        # h_im = 3.98: taken
+    out = msda_ref.forward(d["value"], d["shapes"], d["start"], d["loc"], d["w"])
+    w0 = d["w"].clone(); w0[0, :, 0, 0, 0] = 0                  # dropping the "not taken" taps changes nothing
+    assert_close(msda_ref.forward(d["value"], d["shapes"], d["start"], d["loc"], w0), out, 0, "untaken taps")
+    w1 = d["w"].clone(); w1[0, :, 0, 0, 1] = 0
+    assert np.abs(msda_ref.forward(d["value"], d["shapes"], d["start"], d["loc"], w1) - out).max() > 1e-4
+
+
+def test_module_interface_matches_mmcv_msda_parameters():
+    from simpb_b200 import msda
+    m = msda.QueryGroupMultiScaleDeformableAttention(embed_dims=256, num_heads=8, num_levels=4,
+                                                     num_points=4, num_cams=6)
+    sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert sd == {"sampling_offsets.weight": (256, 256), "sampling_offsets.bias": (256,),
+                  "attention_weights.weight": (128, 256), "attention_weights.bias": (128,),
+                  "value_proj.weight": (256, 256), "value_proj.bias": (256,),
+                  "output_proj.weight": (256, 256), "output_proj.bias": (256,)}
+    assert float(m.sampling_offsets.weight.abs().max()) == 0.0
+    b = m.sampling_offsets.bias.view(8, 4, 4, 2)
+    assert torch.allclose(b[0, 0, :, 0], torch.tensor([1.0, 2.0, 3.0, 4.0]))    # head 0 looks along +x
+
+
+# ------------------------------------------------------------------ GPU: kernels vs the oracle
+def gpu(d, dtype=torch.float32):
+    return dict(value=d["value"].cuda().to(dtype), shapes=d["shapes"].int().cuda(),
+                start=d["start"].int().cuda(), loc=d["loc"].cuda(), w=d["w"].cuda(), go=d["go"].cuda())
+
+
+def check(d, dtype=torch.float32):
+    from simpb_b200 import cabi
+    g = gpu(d, dtype)
+    vref = g["value"].float().cpu()
+    out = cabi.msda_forward(g["value"], g["shapes"], g["start"], g["loc"], g["w"])
+    assert_close(out, msda_ref.forward(vref, d["shapes"], d["start"], d["loc"], d["w"]), RTOL_F32, "forward")
+    gv, gl, gw = cabi.msda_backward(g["value"], g["shapes"], g["start"], g["loc"], g["w"], g["go"])
+    rgv, rgl, rgw = msda_ref.backward(vref, d["shapes"], d["start"], d["loc"], d["w"], d["go"])
+    assert_close(gv, rgv, RTOL_F32, "grad_value")
+    assert_close(gl, rgl, RTOL_F32, "grad_sampling_loc")
+    assert_close(gw, rgw, RTOL_F32, "grad_attn_weight")
+    _, gl2, gw2 = cabi.msda_backward(g["value"], g["shapes"], g["start"], g["loc"], g["w"], g["go"],
+                                     need_value=False)
+    assert torch.equal(gl, gl2) and torch.equal(gw, gw2)          # no atomics: bitwise reproducible
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [
+    dict(bs=2, Q=7, M=4, D=8, sizes=SIZES3, P=4),        # 2 vector lanes per head
+    dict(bs=1, Q=33, M=8, D=32, sizes=SIZES3, P=4),      # SimPB head geometry (8 lanes)
+    dict(bs=1, Q=9, M=8, D=16, sizes=SIZES3, P=3),       # 4 lanes, L*P not a multiple of the batch
+    dict(bs=2, Q=5, M=3, D=4, sizes=SIZES3, P=2),        # 1 lane per head, odd head count: no TMA
+    dict(bs=1, Q=4, M=2, D=5, sizes=((5, 7),), P=3),     # generic kernels
+    dict(bs=1, Q=3, M=16, D=32, sizes=SIZES3, P=8),      # 16 heads, 24 taps per head
+])
+def test_kernels_vs_oracle_small_shapes(cfg):
+    check(make_case(3, **cfg))
+
+
+@pytest.mark.gpu
+def test_kernels_vs_oracle_simpb_shape():
+    """One camera of the R50 704x256 pyramid (14,960 rows x 256), 300 queries, 8 heads x 4 x 4."""
+    from simpb_b200 import synthetic
+    check(make_case(4, bs=2, Q=300, M=8, D=32, sizes=synthetic.R50_LEVELS, P=4, lo=-0.05, hi=1.05))
+
+
+@pytest.mark.gpu
+def test_bf16_value_table():
+    from simpb_b200 import cabi
+    d = make_case(5, bs=1, Q=40, M=8, D=32, sizes=SIZES3, P=4)
+    check(d, torch.bfloat16)
+    g = gpu(d, torch.bfloat16)
+    out = cabi.msda_forward(g["value"], g["shapes"], g["start"], g["loc"], g["w"])
+    assert_close(out, msda_ref.forward(d["value"], d["shapes"], d["start"], d["loc"], d["w"]), RTOL_BF16,
+                 "bf16 value vs fp32 oracle")
+
+
+@pytest.mark.gpu
+def test_autograd_function_and_query_group_module():
+    """The module on camera groups against the same module evaluated with the grid_sample
+    formulation (mmcv's CPU fallback) in fp64 — outputs and every gradient."""
+    from simpb_b200 import msda, synthetic
+    torch.manual_seed(0)
+    bs, cams, C = 2, 3, 64
+    sizes = SIZES3
+    shapes = torch.tensor(sizes)
+    counts = shapes[:, 0] * shapes[:, 1]
+    start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]])
+    S = int(counts.sum())
+    groups = [(0, 5), (5, 5), (5, 12)]                    # camera 1 has no query
+    m = msda.QueryGroupMultiScaleDeformableAttention(embed_dims=C, num_heads=4, num_levels=3, num_points=4,
+                                                     num_cams=cams, query_groups=groups, dropout=0.0,
+                                                     batch_first=True, residual_mode="cat")
+    with torch.no_grad():                                  # the default init makes every query look alike
+        m.sampling_offsets.weight.normal_(0, 0.05)
+        m.attention_weights.weight.normal_(0, 0.5)
+    g = torch.Generator().manual_seed(1)
+    query = torch.randn(bs, 12, C, generator=g)
+    value = torch.randn(bs * cams, S, C, generator=g)
+    ref_pts = torch.rand(bs, 12, 3, 2, generator=g)
+    go = torch.randn(bs, 12, 2 * C, generator=g)
+
+    def run(mod, dev, dt, fn):
+        q = query.to(dev, dt).requires_grad_()
+        v = value.to(dev, dt).requires_grad_()
+        mod = mod.to(dev, dt)
+        mod.zero_grad()
+        val = mod.value_proj(v).view(bs, cams, S, mod.num_heads, -1)
+        off = mod.sampling_offsets(q).view(bs, 12, mod.num_heads, 3, 4, 2)
+        w = mod.attention_weights(q).view(bs, 12, mod.num_heads, 12).softmax(-1).view(bs, 12, mod.num_heads, 3, 4)
+        loc = mod.sampling_locations(ref_pts.to(dev, dt), off, shapes.to(dev))
+        outs = [fn(val[:, i], loc[:, a:b], w[:, a:b]) for i, (a, b) in enumerate(groups) if b > a]
+        out = torch.cat([mod.output_proj(torch.cat(outs, 1)), q], -1)
+        out.backward(go.to(dev, dt))
+        return out, q.grad, v.grad, {n: p.grad.clone() for n, p in mod.named_parameters()}
+
+    ref = run(m, "cpu", torch.float64,
+              lambda val, loc, w: msda_ref.msda_grid_sample(val, shapes, loc, w))
+    m = m.float().cuda()
+    m.zero_grad()
+    q = query.cuda().requires_grad_()
+    v = value.cuda().requires_grad_()
+    out = m(q, value=v, reference_points=ref_pts.cuda(), spatial_shapes=shapes.cuda(),
+            level_start_index=start.cuda())
+    out.backward(go.cuda())
+    assert_close(out, ref[0], RTOL_F32, "module output")
+    assert_close(q.grad, ref[1], 2e-5, "grad query")
+    assert_close(v.grad, ref[2], 2e-5, "grad value")
+    for n, p in m.named_parameters():
+        assert_close(p.grad, ref[3][n], 2e-5, "grad " + n)

@@ -8,7 +8,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from simpb_b200 import build  # noqa: E402
+import importlib.util  # noqa: E402
+_spec = importlib.util.spec_from_file_location("simpb_b200_build", os.path.join(ROOT, "simpb_b200", "build.py"))
+build = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(build)
 
 _, err = build.compile_objects(verbose=True, obj_dir="/tmp/dfa_ptxas_report")
 filt = sys.argv[1] if len(sys.argv) > 1 else ""
