@@ -160,17 +160,21 @@ int dfa_softmax_weights_split_backward(const float *logits_anchor, const float *
  * sampling_loc [bs,Q,M,L,P,2] (x,y), attn_weight [bs,Q,M,L,P] → output [bs,Q,M*D] float32, written
  * (no zero-fill needed).  Backward: grad_sampling_loc and grad_attn_weight are fully written;
  * grad_value [bs,S,M,D] float32 is accumulated into (zero_grad_value != 0: zero-filled on the stream
- * first; NULL: skipped). */
+ * first; NULL: skipped).
+ * Camera groups in ONE launch: with num_tables = K > 1, value is [bs, K, S, M, D] and query q samples
+ * table query_table[q] (int32 [Q], device) — the reference loops over the K groups with one mmcv
+ * call each.  num_tables = 1 / query_table = NULL is the plain function. */
 int dfa_msda_forward(const void *value, int value_dtype, const int32_t *spatial_shapes,
                      const int32_t *level_start_index, const float *sampling_loc,
                      const float *attn_weight, float *output, int bs, int num_value, int num_heads,
-                     int head_dim, int num_query, int num_levels, int num_points, void *stream);
+                     int head_dim, int num_query, int num_levels, int num_points, int num_tables,
+                     const int32_t *query_table, void *stream);
 int dfa_msda_backward(const void *value, int value_dtype, const int32_t *spatial_shapes,
                       const int32_t *level_start_index, const float *sampling_loc,
                       const float *attn_weight, const float *grad_output, float *grad_value,
                       float *grad_sampling_loc, float *grad_attn_weight, int bs, int num_value,
                       int num_heads, int head_dim, int num_query, int num_levels, int num_points,
-                      int zero_grad_value, void *stream);
+                      int num_tables, const int32_t *query_table, int zero_grad_value, void *stream);
 
 /* Forward with HOST buffers: host→device copies of all five inputs, the kernel, and the
  * device→host copy of the output, on `stream`, then a stream synchronise.  Host buffers should

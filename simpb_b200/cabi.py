@@ -56,9 +56,10 @@ def _load():
     lib.dfa_softmax_weights_split.argtypes = [vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.dfa_softmax_weights_split_backward.argtypes = [vp, vp, vp, f32, vp, vp, vp, i32, i32, i32, i32,
                                                        i32, i32, vp]
-    lib.dfa_msda_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.dfa_msda_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32,
+                                     vp, vp]
     lib.dfa_msda_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
-                                      i32, i32, i32, vp]
+                                      i32, i32, i32, vp, i32, vp]
     lib.dfa_forward_host_workspace_bytes.restype = i64
     lib.dfa_forward_host_workspace_bytes.argtypes = [i32, dp]
     lib.dfa_forward_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp, i64, vp]
@@ -351,35 +352,45 @@ def softmax_weights_split_backward(logits_anchor, logits_cam, dims, keep, scale,
     return g_anchor, g_full.sum(dim=1).reshape(logits_cam.shape)
 
 
-def _msda_dims(value, shapes, start, loc, w):
+def _msda_dims(value, shapes, start, loc, w, query_table):
     _need(value, "value"); _need(shapes, "spatial_shapes", torch.int32)
     _need(start, "level_start_index", torch.int32)
     _need(loc, "sampling_locations", torch.float32); _need(w, "attention_weights", torch.float32)
-    if value.dim() != 4 or loc.dim() != 6 or loc.shape[5] != 2 or w.dim() != 5 or shapes.dim() != 2:
-        raise DfaError("msda: value [bs,S,M,D], loc [bs,Q,M,L,P,2], weights [bs,Q,M,L,P] expected")
-    bs, S, M, D = value.shape
+    grouped = query_table is not None
+    if value.dim() != (5 if grouped else 4) or loc.dim() != 6 or loc.shape[5] != 2 or w.dim() != 5 \
+            or shapes.dim() != 2:
+        raise DfaError("msda: value [bs,(K,)S,M,D], loc [bs,Q,M,L,P,2], weights [bs,Q,M,L,P] expected")
+    bs = value.shape[0]
+    K = value.shape[1] if grouped else 1
+    S, M, D = value.shape[-3:]
     Q, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
     if tuple(loc.shape) != (bs, Q, M, L, P, 2) or tuple(w.shape) != (bs, Q, M, L, P) \
             or tuple(shapes.shape) != (L, 2) or start.numel() != L:
         raise DfaError("msda: inconsistent shapes value=%s loc=%s weights=%s shapes=%s"
                        % (tuple(value.shape), tuple(loc.shape), tuple(w.shape), tuple(shapes.shape)))
-    return bs, S, M, D, Q, L, P
+    if grouped:
+        _need(query_table, "query_table", torch.int32)
+        if query_table.numel() != Q:
+            raise DfaError("msda: query_table must hold one table index per query")
+    return bs, S, M, D, Q, L, P, K
 
 
-def msda_forward(value, shapes, start, loc, w):
-    bs, S, M, D, Q, L, P = _msda_dims(value, shapes, start, loc, w)
+def msda_forward(value, shapes, start, loc, w, query_table=None):
+    """value [bs,S,M,D], or [bs,K,S,M,D] with query_table int32 [Q] (table sampled by each query)."""
+    bs, S, M, D, Q, L, P, K = _msda_dims(value, shapes, start, loc, w, query_table)
     out = torch.empty(bs, Q, M * D, device=value.device, dtype=torch.float32)
     if bs == 0 or Q == 0:
         return out
     with torch.cuda.device(value.device):
         check(lib.dfa_msda_forward(value.data_ptr(), feat_dtype(value), shapes.data_ptr(), start.data_ptr(),
-                                   loc.data_ptr(), w.data_ptr(), out.data_ptr(), bs, S, M, D, Q, L, P,
+                                   loc.data_ptr(), w.data_ptr(), out.data_ptr(), bs, S, M, D, Q, L, P, K,
+                                   query_table.data_ptr() if query_table is not None else None,
                                    stream_ptr(value.device)), "dfa_msda_forward")
     return out
 
 
-def msda_backward(value, shapes, start, loc, w, grad_out, need_value=True):
-    bs, S, M, D, Q, L, P = _msda_dims(value, shapes, start, loc, w)
+def msda_backward(value, shapes, start, loc, w, grad_out, need_value=True, query_table=None):
+    bs, S, M, D, Q, L, P, K = _msda_dims(value, shapes, start, loc, w, query_table)
     _need(grad_out, "grad_output", torch.float32)
     if grad_out.numel() != bs * Q * M * D:
         raise DfaError("msda: grad_output must be [bs, Q, M*D]")
@@ -393,7 +404,9 @@ def msda_backward(value, shapes, start, loc, w, grad_out, need_value=True):
         check(lib.dfa_msda_backward(value.data_ptr(), feat_dtype(value), shapes.data_ptr(), start.data_ptr(),
                                     loc.data_ptr(), w.data_ptr(), grad_out.data_ptr(),
                                     gv.data_ptr() if gv is not None else None, gl.data_ptr(), gw.data_ptr(),
-                                    bs, S, M, D, Q, L, P, 1, stream_ptr(value.device)), "dfa_msda_backward")
+                                    bs, S, M, D, Q, L, P, K,
+                                    query_table.data_ptr() if query_table is not None else None, 1,
+                                    stream_ptr(value.device)), "dfa_msda_backward")
     return gv, gl, gw
 
 

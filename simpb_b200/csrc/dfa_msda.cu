@@ -22,7 +22,14 @@ namespace {
 
 struct MsdaDims {
   int bs, S, M, D, Q, L, P;
+  int K;  // value tables per batch item (camera groups); query q reads table qcam[q]
 };
+
+// first element of the value table query (b, q) samples
+__device__ __forceinline__ size_t msda_table(const MsdaDims &d, const int *qcam, int b, int q) {
+  const int cam = qcam ? __ldg(qcam + q) : 0;
+  return (static_cast<size_t>(b) * d.K + cam) * d.S * d.M * d.D;
+}
 
 struct MsdaGeom {
   int idx[4];  // position inside the level (h*W + w), -1 when the corner is outside or the tap is not taken
@@ -78,7 +85,8 @@ template <typename T, int LPG, int U, bool TMA>
 __global__ void __launch_bounds__(1024)
     msda_fwd_kernel(const T *__restrict__ value, const int *__restrict__ shapes,
                     const int *__restrict__ start, const float *__restrict__ loc,
-                    const float *__restrict__ w, float *__restrict__ out, MsdaDims d) {
+                    const float *__restrict__ w, float *__restrict__ out, MsdaDims d,
+                    const int *__restrict__ qcam) {
   constexpr int VEC = FeatVec<T>::VEC;
   constexpr int TPW = 32 / (4 * LPG);
   extern __shared__ __align__(128) unsigned char smem[];
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(1024)
   __syncwarp();
 
   const int j = lane % LPG, q = (lane / LPG) & 3, sub = lane / (4 * LPG);
-  const T *vb = value + static_cast<size_t>(b) * d.S * d.M * d.D + j * VEC;
+  const T *vb = value + msda_table(d, qcam, b, static_cast<int>(bq - static_cast<long long>(b) * d.Q)) + j * VEC;
   float acc[VEC];
 #pragma unroll
   for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(1024)
                     const int *__restrict__ start, const float *__restrict__ loc,
                     const float *__restrict__ w, const float *__restrict__ grad_out,
                     float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                    float *__restrict__ grad_w, MsdaDims d) {
+                    float *__restrict__ grad_w, MsdaDims d, const int *__restrict__ qcam) {
   constexpr int VEC = FeatVec<T>::VEC;
   constexpr int TPW = 32 / (4 * LPG);
   extern __shared__ __align__(128) unsigned char smem[];
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(1024)
   __syncwarp();
 
   const int j = lane % LPG, q = (lane / LPG) & 3, sub = lane / (4 * LPG);
-  const size_t vbase = static_cast<size_t>(b) * d.S * d.M * d.D + j * VEC;
+  const size_t vbase = msda_table(d, qcam, b, static_cast<int>(bq - static_cast<long long>(b) * d.Q)) + j * VEC;
   const T *vb = value + vbase;
   float *gvb = grad_value ? grad_value + vbase : nullptr;
   float go[VEC];
@@ -250,14 +258,15 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     msda_fwd_generic_kernel(const T *__restrict__ value, const int *__restrict__ shapes,
                             const int *__restrict__ start, const float *__restrict__ loc,
-                            const float *__restrict__ w, float *__restrict__ out, MsdaDims d) {
+                            const float *__restrict__ w, float *__restrict__ out, MsdaDims d,
+                            const int *__restrict__ qcam) {
   const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= static_cast<long long>(d.bs) * d.Q * d.M) return;
   const int m = static_cast<int>(wid % d.M);
   const int b = static_cast<int>(wid / d.M / d.Q);
   const int LP = d.L * d.P;
-  const T *vb = value + static_cast<size_t>(b) * d.S * d.M * d.D;
+  const T *vb = value + msda_table(d, qcam, b, static_cast<int>((wid / d.M) % d.Q));
   for (int c0 = 0; c0 < d.D; c0 += 32) {
     const int c = c0 + lane;
     float acc = 0.f;
@@ -283,14 +292,14 @@ __global__ void __launch_bounds__(256)
                             const int *__restrict__ start, const float *__restrict__ loc,
                             const float *__restrict__ w, const float *__restrict__ grad_out,
                             float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                            float *__restrict__ grad_w, MsdaDims d) {
+                            float *__restrict__ grad_w, MsdaDims d, const int *__restrict__ qcam) {
   const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= static_cast<long long>(d.bs) * d.Q * d.M) return;
   const int m = static_cast<int>(wid % d.M);
   const int b = static_cast<int>(wid / d.M / d.Q);
   const int LP = d.L * d.P;
-  const size_t vbase = static_cast<size_t>(b) * d.S * d.M * d.D;
+  const size_t vbase = msda_table(d, qcam, b, static_cast<int>((wid / d.M) % d.Q));
   for (int t = 0; t < LP; ++t) {
     const int l = t / d.P;
     const int H = shapes[2 * l], W = shapes[2 * l + 1];
@@ -323,11 +332,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-int msda_check(int bs, int S, int M, int D, int Q, int L, int P, MsdaDims &d) {
-  if (bs <= 0 || S <= 0 || M <= 0 || D <= 0 || Q <= 0 || L <= 0 || P <= 0) return DFA_ERR_BAD_DIMS;
+int msda_check(int bs, int S, int M, int D, int Q, int L, int P, int K, MsdaDims &d) {
+  if (bs <= 0 || S <= 0 || M <= 0 || D <= 0 || Q <= 0 || L <= 0 || P <= 0 || K <= 0) return DFA_ERR_BAD_DIMS;
   if (static_cast<long long>(S) * M * D >= (1ll << 31)) return DFA_ERR_BAD_DIMS;  // 32-bit offsets per item
   if (static_cast<long long>(bs) * Q * M >= (1ll << 31)) return DFA_ERR_BAD_DIMS;
-  d = MsdaDims{bs, S, M, D, Q, L, P};
+  d = MsdaDims{bs, S, M, D, Q, L, P, K};
   return 0;
 }
 
@@ -353,64 +362,65 @@ constexpr int MSDA_U = 4;
 
 template <typename T, int LPG>
 int msda_launch_fwd(const void *value, const int *shapes, const int *start, const float *loc,
-                    const float *w, float *out, const MsdaDims &d, cudaStream_t st) {
+                    const float *w, float *out, const MsdaDims &d, const int *qcam, cudaStream_t st) {
   constexpr int TPW = 32 / (4 * LPG);
   const uint32_t smem = msda_smem(d, TPW * MSDA_U);
   const bool tma = msda_tma_ok(d, loc, w);
   auto kern = tma ? msda_fwd_kernel<T, LPG, MSDA_U, true> : msda_fwd_kernel<T, LPG, MSDA_U, false>;
   if (int rc = set_smem(kern, smem)) return rc;
-  kern<<<d.bs * d.Q, 32 * d.M, smem, st>>>(static_cast<const T *>(value), shapes, start, loc, w, out, d);
+  kern<<<d.bs * d.Q, 32 * d.M, smem, st>>>(static_cast<const T *>(value), shapes, start, loc, w, out, d,
+                                          qcam);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <typename T, int LPG>
 int msda_launch_bwd(const void *value, const int *shapes, const int *start, const float *loc,
                     const float *w, const float *go, float *gv, float *gl, float *gw, const MsdaDims &d,
-                    cudaStream_t st) {
+                    const int *qcam, cudaStream_t st) {
   constexpr int TPW = 32 / (4 * LPG);
   const uint32_t smem = msda_smem(d, TPW * MSDA_U);
   const bool tma = msda_tma_ok(d, loc, w);
   auto kern = tma ? msda_bwd_kernel<T, LPG, MSDA_U, true> : msda_bwd_kernel<T, LPG, MSDA_U, false>;
   if (int rc = set_smem(kern, smem)) return rc;
   kern<<<d.bs * d.Q, 32 * d.M, smem, st>>>(static_cast<const T *>(value), shapes, start, loc, w, go, gv,
-                                          gl, gw, d);
+                                          gl, gw, d, qcam);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <typename T>
 int msda_forward_typed(const void *value, const int *shapes, const int *start, const float *loc,
-                       const float *w, float *out, const MsdaDims &d, cudaStream_t st) {
+                       const float *w, float *out, const MsdaDims &d, const int *qcam, cudaStream_t st) {
   const int lpg = msda_lpg<T>(d, value);
   if (lpg && aligned(out, 16) && msda_smem(d, 32) <= 200u * 1024u) {
     switch (lpg) {
-      case 8: return msda_launch_fwd<T, 8>(value, shapes, start, loc, w, out, d, st);
-      case 4: return msda_launch_fwd<T, 4>(value, shapes, start, loc, w, out, d, st);
-      case 2: return msda_launch_fwd<T, 2>(value, shapes, start, loc, w, out, d, st);
-      default: return msda_launch_fwd<T, 1>(value, shapes, start, loc, w, out, d, st);
+      case 8: return msda_launch_fwd<T, 8>(value, shapes, start, loc, w, out, d, qcam, st);
+      case 4: return msda_launch_fwd<T, 4>(value, shapes, start, loc, w, out, d, qcam, st);
+      case 2: return msda_launch_fwd<T, 2>(value, shapes, start, loc, w, out, d, qcam, st);
+      default: return msda_launch_fwd<T, 1>(value, shapes, start, loc, w, out, d, qcam, st);
     }
   }
   const long long warps = static_cast<long long>(d.bs) * d.Q * d.M;
   msda_fwd_generic_kernel<T><<<static_cast<int>((warps + 7) / 8), 256, 0, st>>>(
-      static_cast<const T *>(value), shapes, start, loc, w, out, d);
+      static_cast<const T *>(value), shapes, start, loc, w, out, d, qcam);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <typename T>
 int msda_backward_typed(const void *value, const int *shapes, const int *start, const float *loc,
                         const float *w, const float *go, float *gv, float *gl, float *gw,
-                        const MsdaDims &d, cudaStream_t st) {
+                        const MsdaDims &d, const int *qcam, cudaStream_t st) {
   const int lpg = msda_lpg<T>(d, value);
   if (lpg && aligned(go, 16) && aligned(gv, 16) && aligned(gl, 8) && msda_smem(d, 32) <= 200u * 1024u) {
     switch (lpg) {
-      case 8: return msda_launch_bwd<T, 8>(value, shapes, start, loc, w, go, gv, gl, gw, d, st);
-      case 4: return msda_launch_bwd<T, 4>(value, shapes, start, loc, w, go, gv, gl, gw, d, st);
-      case 2: return msda_launch_bwd<T, 2>(value, shapes, start, loc, w, go, gv, gl, gw, d, st);
-      default: return msda_launch_bwd<T, 1>(value, shapes, start, loc, w, go, gv, gl, gw, d, st);
+      case 8: return msda_launch_bwd<T, 8>(value, shapes, start, loc, w, go, gv, gl, gw, d, qcam, st);
+      case 4: return msda_launch_bwd<T, 4>(value, shapes, start, loc, w, go, gv, gl, gw, d, qcam, st);
+      case 2: return msda_launch_bwd<T, 2>(value, shapes, start, loc, w, go, gv, gl, gw, d, qcam, st);
+      default: return msda_launch_bwd<T, 1>(value, shapes, start, loc, w, go, gv, gl, gw, d, qcam, st);
     }
   }
   const long long warps = static_cast<long long>(d.bs) * d.Q * d.M;
   msda_bwd_generic_kernel<T><<<static_cast<int>((warps + 7) / 8), 256, 0, st>>>(
-      static_cast<const T *>(value), shapes, start, loc, w, go, gv, gl, gw, d);
+      static_cast<const T *>(value), shapes, start, loc, w, go, gv, gl, gw, d, qcam);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -421,19 +431,22 @@ extern "C" {
 int dfa_msda_forward(const void *value, int value_dtype, const int32_t *spatial_shapes,
                      const int32_t *level_start_index, const float *sampling_loc,
                      const float *attn_weight, float *output, int bs, int num_value, int num_heads,
-                     int head_dim, int num_query, int num_levels, int num_points, void *stream) {
+                     int head_dim, int num_query, int num_levels, int num_points, int num_tables,
+                     const int32_t *query_table, void *stream) {
   if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output)
     return DFA_ERR_NULL_POINTER;
   MsdaDims d;
-  if (int rc = msda_check(bs, num_value, num_heads, head_dim, num_query, num_levels, num_points, d))
+  if (num_tables > 1 && !query_table) return DFA_ERR_NULL_POINTER;
+  if (int rc = msda_check(bs, num_value, num_heads, head_dim, num_query, num_levels, num_points,
+                          num_tables, d))
     return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (value_dtype == DFA_F32)
     return msda_forward_typed<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                                     output, d, st);
+                                     output, d, query_table, st);
   if (value_dtype == DFA_BF16)
     return msda_forward_typed<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_loc,
-                                             attn_weight, output, d, st);
+                                             attn_weight, output, d, query_table, st);
   return DFA_ERR_BAD_DTYPE;
 }
 
@@ -442,26 +455,29 @@ int dfa_msda_backward(const void *value, int value_dtype, const int32_t *spatial
                       const float *attn_weight, const float *grad_output, float *grad_value,
                       float *grad_sampling_loc, float *grad_attn_weight, int bs, int num_value,
                       int num_heads, int head_dim, int num_query, int num_levels, int num_points,
-                      int zero_grad_value, void *stream) {
+                      int num_tables, const int32_t *query_table, int zero_grad_value, void *stream) {
   if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
       !grad_sampling_loc || !grad_attn_weight)
     return DFA_ERR_NULL_POINTER;  // grad_value may be NULL: the value gradient is skipped
   MsdaDims d;
-  if (int rc = msda_check(bs, num_value, num_heads, head_dim, num_query, num_levels, num_points, d))
+  if (num_tables > 1 && !query_table) return DFA_ERR_NULL_POINTER;
+  if (int rc = msda_check(bs, num_value, num_heads, head_dim, num_query, num_levels, num_points,
+                          num_tables, d))
     return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (zero_grad_value && grad_value) {
-    cudaError_t e = cudaMemsetAsync(grad_value, 0,
-                                    sizeof(float) * static_cast<size_t>(bs) * num_value * num_heads * head_dim, st);
+    cudaError_t e = cudaMemsetAsync(
+        grad_value, 0, sizeof(float) * static_cast<size_t>(bs) * num_tables * num_value * num_heads * head_dim, st);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   if (value_dtype == DFA_F32)
     return msda_backward_typed<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                                      grad_output, grad_value, grad_sampling_loc, grad_attn_weight, d, st);
+                                      grad_output, grad_value, grad_sampling_loc, grad_attn_weight, d,
+                                      query_table, st);
   if (value_dtype == DFA_BF16)
     return msda_backward_typed<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_loc,
                                               attn_weight, grad_output, grad_value, grad_sampling_loc,
-                                              grad_attn_weight, d, st);
+                                              grad_attn_weight, d, query_table, st);
   return DFA_ERR_BAD_DTYPE;
 }
 

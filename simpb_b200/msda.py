@@ -52,6 +52,34 @@ class MultiScaleDeformableAttnFunction(Function):
         return gv, None, None, gl, gw, None
 
 
+class GroupedMultiScaleDeformableAttnFunction(Function):
+    """All camera groups in one launch: value [bs, K, S, M, D], query_table int32 [Q] names the
+    table each query samples (the reference calls mmcv once per group and concatenates)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, query_table):
+        if value.dtype != torch.bfloat16:
+            value = value.float()
+        value = value.contiguous()
+        shapes, start = _i32(value_spatial_shapes), _i32(value_level_start_index)
+        loc = sampling_locations.contiguous().float()
+        w = attention_weights.contiguous().float()
+        query_table = _i32(query_table)
+        ctx.save_for_backward(value, shapes, start, loc, w, query_table)
+        return cabi.msda_forward(value, shapes, start, loc, w, query_table)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, start, loc, w, query_table = ctx.saved_tensors
+        gv, gl, gw = cabi.msda_backward(value, shapes, start, loc, w, grad_output.contiguous().float(),
+                                        need_value=ctx.needs_input_grad[0], query_table=query_table)
+        if gv is not None and value.dtype != torch.float32:
+            gv = gv.to(value.dtype)
+        return gv, None, None, gl, gw, None
+
+
 class QueryGroupMultiScaleDeformableAttention(nn.Module):
     """group_attn.py:136-256.  Queries are partitioned into per-camera groups
     (`query_groups[i] = (q0, q1)` samples camera i); value is `[bs*num_cams, S, C]` when
@@ -93,6 +121,26 @@ class QueryGroupMultiScaleDeformableAttention(nn.Module):
         nn.init.constant_(self.value_proj.bias, 0.0)
         nn.init.xavier_uniform_(self.output_proj.weight)
         nn.init.constant_(self.output_proj.bias, 0.0)
+
+    def _query_table(self, num_query, device):
+        """int32 [num_query] camera index per query when the groups tile the queries in order
+        (what the reference's allocation produces), else None.  Cached per (groups, device)."""
+        groups = tuple((int(a), int(b)) for a, b in self.query_groups)
+        key = (groups, num_query, str(device))
+        if getattr(self, "_table_key", None) == key:
+            return self._table
+        pos, cams = 0, []
+        for i, (a, b) in enumerate(groups):
+            if b <= a:
+                continue
+            if a != pos or i >= self.num_cams:
+                pos = -1
+                break
+            cams += [i] * (b - a)
+            pos = b
+        table = torch.tensor(cams, dtype=torch.int32, device=device) if pos == num_query else None
+        self._table_key, self._table = key, table
+        return table
 
     def sampling_locations(self, reference_points, sampling_offsets, spatial_shapes):
         """group_attn.py:191-217."""
@@ -137,13 +185,19 @@ class QueryGroupMultiScaleDeformableAttention(nn.Module):
             loc[xs, ys] = 0
         if kwargs.get("query_groups", None) is not None:
             self.query_groups = kwargs["query_groups"]
-        outs = []
-        for i, qg in enumerate(self.query_groups):
-            if qg[1] - qg[0] > 0:
-                outs.append(MultiScaleDeformableAttnFunction.apply(
-                    value[:, i], spatial_shapes, level_start_index, loc[:, qg[0]:qg[1]],
-                    weights[:, qg[0]:qg[1]], self.im2col_step))
-        output = self.output_proj(torch.cat(outs, dim=1))
+        table = self._query_table(num_query, value.device)
+        if table is not None:       # the groups tile [0, num_query) in order: one launch for all cameras
+            output = GroupedMultiScaleDeformableAttnFunction.apply(value, spatial_shapes, level_start_index,
+                                                                   loc, weights, table)
+        else:                       # anything else: group by group, as the reference (:226-236)
+            outs = []
+            for i, qg in enumerate(self.query_groups):
+                if qg[1] - qg[0] > 0:
+                    outs.append(MultiScaleDeformableAttnFunction.apply(
+                        value[:, i], spatial_shapes, level_start_index, loc[:, qg[0]:qg[1]],
+                        weights[:, qg[0]:qg[1]], self.im2col_step))
+            output = torch.cat(outs, dim=1)
+        output = self.output_proj(output)
         if not self.batch_first:
             output = output.permute(1, 0, 2)
         output = self.dropout(output)

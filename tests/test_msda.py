@@ -113,6 +113,32 @@ def test_kernels_vs_oracle_simpb_shape():
 
 
 @pytest.mark.gpu
+def test_grouped_launch_equals_per_group_calls():
+    """value [bs,K,S,M,D] + query_table in one launch == the reference's loop over camera groups."""
+    from simpb_b200 import cabi
+    d = make_case(6, bs=2, Q=30, M=8, D=32, sizes=SIZES3, P=4)
+    g = gpu(d)
+    K = 3
+    gen = torch.Generator().manual_seed(7)
+    value = torch.randn(2, K, d["value"].shape[1], 8, 32, generator=gen).cuda()
+    groups = [(0, 11), (11, 11), (11, 30)]
+    table = torch.tensor([0] * 11 + [2] * 19, dtype=torch.int32).cuda()
+    out = cabi.msda_forward(value, g["shapes"], g["start"], g["loc"], g["w"], table)
+    gv, gl, gw = cabi.msda_backward(value, g["shapes"], g["start"], g["loc"], g["w"], g["go"], query_table=table)
+    for i, (a, b) in enumerate(groups):
+        if b == a:
+            assert float(gv[:, i].abs().max()) == 0.0
+            continue
+        sl = lambda t: t[:, a:b].contiguous()  # noqa: E731
+        o = cabi.msda_forward(value[:, i].contiguous(), g["shapes"], g["start"], sl(g["loc"]), sl(g["w"]))
+        assert torch.equal(out[:, a:b], o)
+        v2, l2, w2 = cabi.msda_backward(value[:, i].contiguous(), g["shapes"], g["start"], sl(g["loc"]),
+                                        sl(g["w"]), sl(g["go"]))
+        assert torch.equal(gl[:, a:b], l2) and torch.equal(gw[:, a:b], w2)
+        assert_close(gv[:, i], v2, 1e-6, "grad_value of group %d" % i)
+
+
+@pytest.mark.gpu
 def test_bf16_value_table():
     from simpb_b200 import cabi
     d = make_case(5, bs=1, Q=40, M=8, D=32, sizes=SIZES3, P=4)
