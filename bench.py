@@ -344,6 +344,22 @@ def run_own_arm(args):
                     "algorithmic_bytes": b_alg, "distinct_rows": sum(u) / len(u),
                     "peak_source": peak_src,
                     "whole_pyramid_variant": {"bytes": b_full, "achieved": achf, "frac": achf / peak}}
+        else:
+            # forward + backward of the op: the forward's bytes, plus for the backward
+            # 2 x locations + 2 x weights + grad_out + the referenced rows once more + the zero fill of
+            # grad_mc_ms_feat + the read-modify-write of the touched gradient rows
+            d0 = host[0]
+            bs, A, P, K, _ = d0["sampling_location"].shape
+            L, G = d0["weights"].shape[4:6]
+            C, U = 256, sum(u) / len(u)
+            b_bwd = (2 * 8 * bs * A * P * K + 2 * 4 * bs * A * P * K * L * G + 4 * bs * A * C
+                     + U * C * esz + bs * d0["num_feat"] * C * 4 + 2 * U * C * 4)
+            ach = (b_alg + b_bwd) / (ms_step * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "kernel": "dfa_fwd_rows_kernel + grad fill + dfa_bwd_merge_kernel",
+                    "kernel_us": ms_step * 1e3, "algorithmic_bytes": b_alg + b_bwd,
+                    "distinct_rows": U, "peak_source": peak_src,
+                    "note": "whole training step of the op (all-reduce overlapped when n_gpus > 1)"}
         line = {"metric": METRIC if args.workload == "fwd" else "deformable_aggregation_fwd_bwd_queries_per_sec",
                 "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,

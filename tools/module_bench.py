@@ -13,7 +13,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import module_ref  # noqa: E402
-from simpb_b200 import blocks, deformable_aggregation_function, feature_maps_format, synthetic  # noqa: E402
+from simpb_b200 import blocks, deformable_aggregation_function, feature_maps_format, msda, synthetic  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1)
@@ -95,6 +95,28 @@ def timeit(fn, graph):
     return e0.elapsed_time(e1) / (reps * len(frames))
 
 
+# the 2-D branch of the released decoder: 3 x QueryGroupMultiScaleDeformableAttention on ~1000 2-D
+# queries split over the 6 cameras, reading the same channel-last table
+msda_layers = [msda.QueryGroupMultiScaleDeformableAttention(256, 8, 4, 4, 6, dropout=0.0, batch_first=True,
+                                                            residual_mode="cat").cuda().eval() for _ in range(3)]
+Q2 = 1008
+groups = [(i * Q2 // 6, (i + 1) * Q2 // 6) for i in range(6)]
+gen = torch.Generator().manual_seed(5)
+q2d = torch.randn(a.batch, Q2, 256, generator=gen).cuda()
+ref2d = torch.rand(a.batch, Q2, 4, 2, generator=gen).cuda()
+
+
+def run_both(g):
+    x = run_fused(g)
+    col, sh, st = g["fm"]
+    value = col.reshape(a.batch, 6, -1, 256).flatten(0, 1)            # simpb_head.py:282-292
+    y = q2d
+    for m in msda_layers:
+        y = m(y, value=value, reference_points=ref2d, spatial_shapes=sh[0], level_start_index=st[0],
+              query_groups=groups)[..., :256]
+    return x, y
+
+
 with torch.no_grad():
     err = float((run_fused(frames[0]) - run_ref(frames[0])).abs().max() / run_ref(frames[0]).abs().max())
 out = {"config": "3 x DFA (released SimPB+ R50 config), bs=%d, 900 anchors, eval" % a.batch,
@@ -108,4 +130,6 @@ for name, fn in (("fused", run_fused), ("torch_front_end", run_ref)):
             out[key] = None           # tensor per call): it cannot be captured into a CUDA graph
             out[key + "_error"] = str(e).split(".")[0][:120]
             torch.cuda.synchronize()
+out["dfa_plus_msda_graph_ms_per_frame"] = round(timeit(run_both, True), 4)
+out["dfa_plus_msda_frames_per_s"] = round(1e3 / out["dfa_plus_msda_graph_ms_per_frame"], 1)
 print(json.dumps(out))
