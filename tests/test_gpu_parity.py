@@ -175,6 +175,36 @@ def test_every_backward_kernel_variant_vs_oracle(variant, monkeypatch):
     check_case(cases[2], dtype=torch.bfloat16)
 
 
+def test_fuzz_random_shapes_vs_oracle():
+    """60 seeded random configurations — group counts, channels per group, levels of odd sizes,
+    1..7 cameras, 1..40 key points, fp32 / bf16 tables, sparse to dense masks — forward and all three
+    gradients against the oracle.  Covers every dispatch path (row-sliced, merging, per-group, generic,
+    TMA and plain staging)."""
+    import random
+    rng = random.Random(1234)
+    seen = set()
+    for case in range(60):
+        G = rng.choice([1, 2, 3, 4, 8, 8, 8, 16])
+        cpg = rng.choice([1, 2, 4, 8, 16, 32, 32, 5])
+        C = G * cpg
+        if C > 512:
+            continue
+        L = rng.randint(1, 4)
+        sizes = tuple((rng.randint(1, 9), rng.randint(1, 13)) for _ in range(L))
+        K, P = rng.randint(1, 7), rng.choice([1, 2, 3, 5, 13, 13, 20, 40])
+        A, bs = rng.randint(1, 12), rng.randint(1, 3)
+        lo, hi = rng.choice([(-0.15, 1.15), (0.05, 0.95), (-1.0, 2.0), (0.4, 0.6)])
+        d = small_case(1000 + case, bs=bs, A=A, P=P, K=K, sizes=sizes, C=C, G=G, lo=lo, hi=hi)
+        dtype = torch.bfloat16 if case % 4 == 3 else torch.float32
+        seen.add((C * (2 if dtype == torch.bfloat16 else 4), G))
+        try:
+            check_case(d, dtype=dtype)
+        except AssertionError as e:
+            raise AssertionError("case %d: bs=%d A=%d P=%d K=%d sizes=%s C=%d G=%d %s: %s"
+                                 % (case, bs, A, P, K, sizes, C, G, dtype, e))
+    assert (1024, 8) in seen and (512, 8) in seen          # the merging / row-sliced fast paths were hit
+
+
 def test_training_anchor_count_vs_oracle():
     from simpb_b200 import synthetic
     check_case(synthetic.rig_op_inputs(bs=1, A=1220, seed=4))
