@@ -24,6 +24,7 @@
  *                          branch, with the broadcast add folded into the kernel
  *   dfa_msda_forward / _backward     mmcv-full 1.7.1 MultiScaleDeformableAttnFunction as called at
  *                          models/group_attn.py:229-233 (third-party kernel, not vendored)
+ *   dfa_forward_fused      models/blocks.py:118-147 in one launch (inference)
  *   dfa_forward_host       the same forward, called with HOST buffers (copies inside)
  *
  * Tensor layouts (row-major, innermost last) — ops/src/deformable_aggregation.cpp:22-28:
@@ -92,6 +93,20 @@ int dfa_backward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_
                  const float *weights, const float *grad_output, float *grad_mc_ms_feat,
                  float *grad_sampling_location, float *grad_weights, const dfa_dims *dims,
                  int flags, void *stream);
+
+/* The module's forward in ONE kernel (inference): key points + camera projection (as
+ * dfa_keypoints_project), softmax over cams x levels x points of the attention logits (as
+ * dfa_softmax_weights[_split], no keep mask) and the aggregation.  logits_anchor is [bs,A,L*P*G]
+ * with logits_cam [bs,K,L*P*G] (split form), or the full [bs,A,K,L*P*G] tensor with
+ * logits_cam = NULL.  sampling_location_out (may be NULL) receives the [bs,A,P,K,2] locations.
+ * Replaces models/blocks.py:118-147 (everything between the Linear layers).  Returns
+ * DFA_ERR_UNSUPPORTED for shapes outside the row-sliced fast path or G not a power of two <= 32:
+ * the caller then runs the three separate entry points. */
+int dfa_forward_fused(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_shape,
+                      const int32_t *scale_start_index, const float *anchor, const float *fix_scale,
+                      int num_fix, const float *learnable_logits, const float *projection_mat,
+                      const float *image_wh, const float *logits_anchor, const float *logits_cam,
+                      float *output, float *sampling_location_out, const dfa_dims *dims, void *stream);
 
 /* Test side channel: the geometry the kernels use, for the bit-exact checks.
  * valid [bs,A,P,K] uint8; corner_rows [bs,A,P,K,L,4] int32 (row in [0,num_feat) or -1). */

@@ -278,10 +278,38 @@ class DeformableFeatureAggregation(nn.Module):
                                       keep, scale)
         return loc, w
 
+    def fused_features(self, instance_feature, anchor, anchor_embed, feature_maps, metas):
+        """Inference path: key points, projection, softmax and aggregation in ONE launch
+        (dfa_forward_fused); None when the shape is outside that kernel's fast path."""
+        bs, A = instance_feature.shape[:2]
+        col, shape, start = feature_maps
+        if col.dtype != torch.bfloat16:
+            col = col.float()
+        gen = self.kps_generator
+        logits_a = self.weights_fc(instance_feature + anchor_embed)
+        logits_k = None
+        if self.camera_encoder is not None:
+            cam = self.camera_encoder(metas["projection_mat"][:, :, :3].reshape(bs, self.num_cams, -1))
+            logits_k = nn.functional.linear(cam, self.weights_fc.weight).contiguous().float()
+        off = gen.offset_logits(instance_feature)
+        wh = metas.get("image_wh")
+        i32 = lambda t: t if t.dtype == torch.int32 and t.is_contiguous() else t.contiguous().int()  # noqa: E731
+        f32 = lambda t: None if t is None else t.contiguous().float()  # noqa: E731
+        return cabi.forward_fused(col.contiguous(), i32(shape), i32(start), f32(anchor), f32(gen.fix_scale),
+                                  f32(off), f32(metas["projection_mat"]), f32(wh), f32(logits_a), logits_k,
+                                  (bs, A, self.num_cams, self.num_levels, self.num_pts, self.num_groups))
+
     def forward(self, instance_feature, anchor, anchor_embed, feature_maps, metas, **kwargs):
-        loc, w = self.sampling_and_weights(instance_feature, anchor, anchor_embed, metas,
-                                           keep=kwargs.get("attn_keep_mask"))
-        features = DAF(*feature_maps, loc, w)
+        features = None
+        keep = kwargs.get("attn_keep_mask")
+        no_grad = not torch.is_grad_enabled() or not (
+            instance_feature.requires_grad or anchor.requires_grad or anchor_embed.requires_grad
+            or feature_maps[0].requires_grad or any(p.requires_grad for p in self.parameters()))
+        if keep is None and not (self.training and self.attn_drop > 0) and no_grad:
+            features = self.fused_features(instance_feature, anchor, anchor_embed, feature_maps, metas)
+        if features is None:
+            loc, w = self.sampling_and_weights(instance_feature, anchor, anchor_embed, metas, keep=keep)
+            features = DAF(*feature_maps, loc, w)
         output = self.proj_drop(self.output_proj(features))
         if self.residual_mode == "add":
             output = output + instance_feature

@@ -16,7 +16,8 @@ F32, BF16 = 0, 1
 BWD_ACCUMULATE, BWD_OVERWRITE_SMALL, BWD_ZERO_GRAD_FEAT = 0, 1, 2
 
 # every symbol include/dfa_b200.h declares (tests check the library exports each of them)
-SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_forward", "dfa_backward", "dfa_debug_indices",
+SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_forward", "dfa_backward", "dfa_forward_fused",
+           "dfa_debug_indices",
            "dfa_flatten_maps", "dfa_keypoints_project", "dfa_keypoints_project_backward",
            "dfa_softmax_weights", "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
            "dfa_softmax_weights_split_backward",
@@ -45,6 +46,8 @@ def _load():
     lib.dfa_error_string.argtypes = [i32]
     lib.dfa_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp]
     lib.dfa_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, dp, i32, vp]
+    lib.dfa_forward_fused.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, dp, vp]
+    lib.dfa_forward_fused.restype = i32
     lib.dfa_debug_indices.argtypes = [vp, vp, vp, vp, vp, dp, vp]
     lib.dfa_flatten_maps.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp]
     lib.dfa_keypoints_project.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
@@ -240,6 +243,53 @@ def keypoints_project(anchor, fix_scale, learnable_logits, projection_mat, image
             kp.data_ptr() if kp is not None else None, loc.data_ptr(), bs, A, P, K,
             stream_ptr(anchor.device)), "dfa_keypoints_project")
     return (loc, kp) if want_key_points else loc
+
+
+UNSUPPORTED = -5   # DFA_ERR_UNSUPPORTED
+
+
+def forward_fused(feat, shape, start, anchor, fix_scale, learnable_logits, projection_mat, image_wh,
+                  logits_anchor, logits_cam, dims6, want_locations=False):
+    """The module's forward between its Linear layers in one launch (inference).  dims6 =
+    (bs, A, K, L, P, G).  Returns the aggregated features [bs,A,C] (and the sampling locations), or
+    None when the shape is outside the fused kernel's fast path (the caller then uses the separate
+    kernels)."""
+    _need(feat, "mc_ms_feat"); _need(shape, "spatial_shape", torch.int32)
+    _need(start, "scale_start_index", torch.int32)
+    for t, n in ((anchor, "anchor"), (fix_scale, "fix_scale"), (projection_mat, "projection_mat"),
+                 (logits_anchor, "logits_anchor")):
+        _need(t, n, torch.float32)
+    for t, n in ((learnable_logits, "learnable_logits"), (image_wh, "image_wh"), (logits_cam, "logits_cam")):
+        if t is not None:
+            _need(t, n, torch.float32)
+    bs, A, K, L, P, G = dims6
+    lpg = L * P * G
+    if feat.dim() != 3 or feat.shape[0] != bs or tuple(anchor.shape) != (bs, A, 11) \
+            or tuple(shape.shape) != (K, L, 2) or projection_mat.numel() != bs * K * 16:
+        raise DfaError("forward_fused: inconsistent shapes")
+    if logits_anchor.numel() != (bs * A * lpg if logits_cam is not None else bs * A * K * lpg) \
+            or (logits_cam is not None and logits_cam.numel() != bs * K * lpg):
+        raise DfaError("forward_fused: logits must be [bs,A,L*P*G] + [bs,K,L*P*G] or [bs,A,K,L*P*G]")
+    F_ = fix_scale.shape[0]
+    n_learn = 0 if learnable_logits is None else learnable_logits.numel() // max(bs * A * 3, 1)
+    if F_ + n_learn != P:
+        raise DfaError("forward_fused: fixed + learnable key points != num_pts")
+    d = Dims(bs, K, feat.shape[1], feat.shape[2], L, A, P, G)
+    out = torch.empty(bs, A, feat.shape[2], device=feat.device, dtype=torch.float32)
+    loc = torch.empty(bs, A, P, K, 2, device=feat.device) if want_locations else None
+    if bs == 0 or A == 0:
+        return (out, loc) if want_locations else out
+    ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+    with torch.cuda.device(feat.device):
+        rc = lib.dfa_forward_fused(feat.data_ptr(), feat_dtype(feat), shape.data_ptr(), start.data_ptr(),
+                                   anchor.data_ptr(), fix_scale.data_ptr(), F_, ptr(learnable_logits),
+                                   projection_mat.data_ptr(), ptr(image_wh), logits_anchor.data_ptr(),
+                                   ptr(logits_cam), out.data_ptr(), ptr(loc), ctypes.byref(d),
+                                   stream_ptr(feat.device))
+    if rc == UNSUPPORTED:
+        return None
+    check(rc, "dfa_forward_fused")
+    return (out, loc) if want_locations else out
 
 
 def _kp_dims(anchor, fix_scale, learnable_logits, projection_mat):

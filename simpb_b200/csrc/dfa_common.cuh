@@ -229,6 +229,69 @@ __device__ __forceinline__ int stage_and_compact(const float *__restrict__ loc_g
 }
 
 // ------------------------------------------------------------------------------------------
+// key points and camera projection (shared by the stand-alone front-end kernel and the fused forward)
+// ------------------------------------------------------------------------------------------
+// models/detection3d/blocks.py:181-207: size = exp(anchor[W,L,H]); offset = fix_scale[p] or
+// sigmoid(logit) - 0.5; rotate by yaw, add the centre.  `lg` = this anchor's (P - num_fix) * 3
+// learnable-offset logits (NULL when there are none).
+__device__ __forceinline__ void key_point(const float *an, const float *fix_scale, int num_fix,
+                                          const float *lg, int p, float &x, float &y, float &z) {
+  const float sx = expf(an[3]), sy = expf(an[4]), sz = expf(an[5]);  // W, L, H
+  float ox, oy, oz;
+  if (p < num_fix) {
+    ox = fix_scale[3 * p], oy = fix_scale[3 * p + 1], oz = fix_scale[3 * p + 2];
+  } else {
+    lg += (p - num_fix) * 3;
+    ox = 1.f / (1.f + expf(-lg[0])) - 0.5f;
+    oy = 1.f / (1.f + expf(-lg[1])) - 0.5f;
+    oz = 1.f / (1.f + expf(-lg[2])) - 0.5f;
+  }
+  ox *= sx, oy *= sy, oz *= sz;
+  const float sn = an[6], cs = an[7];
+  x = fmaf(cs, ox, -sn * oy) + an[0];
+  y = fmaf(sn, ox, cs * oy) + an[1];
+  z = oz + an[2];
+}
+
+// models/blocks.py:198-213: m = 4x4 projection matrix (row-major), divide by clamp(depth, 1e-5) and
+// by the image size (wh = (w, h), may be NULL).  The 4-term dot products are evaluated left to
+// right with fused multiply-adds.
+__device__ __forceinline__ void project_point(const float *m, const float *wh, float x, float y, float z,
+                                              float &px, float &py) {
+  const float u = fmaf(m[2], z, fmaf(m[1], y, m[0] * x)) + m[3];
+  const float v = fmaf(m[6], z, fmaf(m[5], y, m[4] * x)) + m[7];
+  const float dpt = fmaf(m[10], z, fmaf(m[9], y, m[8] * x)) + m[11];
+  const float den = fmaxf(dpt, 1e-5f);
+  px = u / den, py = v / den;
+  if (wh) px /= wh[0], py /= wh[1];
+}
+
+// Reduction over the threads that own the same group (tid % G, G a power of two <= 32 here): xor
+// shuffles inside the warp, then one shared-memory row per warp.
+template <int NT>
+__device__ __forceinline__ float group_reduce(float v, float *s_red, int tid, int G, bool is_max) {
+  if (G <= 32 && (G & (G - 1)) == 0) {
+    for (int m = G; m < 32; m <<= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, v, m);
+      v = is_max ? fmaxf(v, o) : v + o;
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    if (lane < G) s_red[warp * G + lane] = v;
+    __syncthreads();
+    float r = s_red[lane % G];
+    for (int w = 1; w < NT / 32; ++w) r = is_max ? fmaxf(r, s_red[w * G + lane % G]) : r + s_red[w * G + lane % G];
+    __syncthreads();
+    return r;
+  }
+  s_red[tid] = v;
+  __syncthreads();
+  float r = s_red[tid % G];
+  for (int j = (tid % G) + G; j < NT; j += G) r = is_max ? fmaxf(r, s_red[j]) : r + s_red[j];
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
 // row-merging kernels: shared constants and shared-memory layout
 // ------------------------------------------------------------------------------------------
 constexpr int MERGE_CAP = 64;     // slots per warp list and round (two chunks)

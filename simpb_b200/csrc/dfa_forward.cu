@@ -270,6 +270,252 @@ __global__ void __launch_bounds__(NT, MINB)
 }
 
 
+#ifdef DFA_PHASE_TIMING
+// Tool-only build (tools/phase_timing.py): per-warp clock64() stamps at the phase boundaries of the
+// merging forward kernel, written to a caller-provided buffer [anchor][warp][8].
+__device__ long long *g_phase_buf = nullptr;
+#define DFA_STAMP(i)                                                                      \
+  do {                                                                                    \
+    if (g_phase_buf && lane == 0)                                                         \
+      g_phase_buf[(static_cast<size_t>(blockIdx.x) * NW + warp) * 8 + (i)] = clock64();   \
+  } while (0)
+#else
+#define DFA_STAMP(i) do {} while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------
+// fused module forward: key points + projection + softmax of the attention logits + gather
+// ------------------------------------------------------------------------------------------
+// The row-sliced kernel with the module's front end folded into its prologue (inference): instead
+// of reading sampling locations and softmaxed weights that three earlier kernels wrote, the CTA
+// takes the anchor (11 floats), the learnable-offset logits and the attention LOGITS and computes
+//   * the anchor's P key points and their K camera projections (same device code as
+//     dfa_keypoints_project, so the sampling locations are bit-identical),
+//   * exp(logit - max) for the K*L*P*G logits, kept UN-normalised in shared memory in their natural
+//     (k,l,p,g) order; the softmax denominator is per (anchor, group), so it is applied once to the
+//     finished output channels instead of to 2,496 weights,
+// and then gathers exactly as dfa_fwd_rows_kernel does.  Neither the [bs,A,P,K,2] locations nor the
+// 9 MB [bs,A,P,K,L,G] weights tensor exist.  Logits may be split (weights_fc linearity, see the
+// front-end file): logits_a [bs,A,L*P*G] + logits_k [bs,K,L*P*G]; logits_k = NULL means logits_a is
+// the full [bs,A,K,L*P*G] tensor.
+struct FusedArgs {
+  const float *anchor, *fix_scale, *off_logits, *proj, *wh, *logits_a, *logits_k;
+  float *loc_out;  // optional [bs,A,P,K,2] copy of the sampling locations (tests)
+  int num_fix;
+};
+
+struct SmemLayoutF {
+  SmemLayout2 r;
+  uint32_t kp, red, inv, la, total;
+};
+__host__ __device__ inline SmemLayoutF smem_layout_fused(int P, int K, int L, int G, int C, int slices,
+                                                         int nt) {
+  SmemLayoutF s;
+  s.r = smem_layout2(P, K, L, G, C, slices, slices);
+  uint32_t o = s.r.total;
+  s.kp = o, o = align_up(o + 12u * P, 16);
+  s.red = o, o = align_up(o + 4u * nt, 16);
+  s.inv = o, o = align_up(o + 4u * G, 16);
+  s.la = o, o = align_up(o + 4u * L * P * G, 16);
+  s.total = o;
+  return s;
+}
+
+template <typename T, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+    dfa_fwd_fused_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
+                         const int *__restrict__ start, FusedArgs fa, float *__restrict__ out, Dims d,
+                         int vpr_log2) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int vpr = 1 << vpr_log2;
+  const int slices = NT >> vpr_log2;
+  const SmemLayoutF layf = smem_layout_fused(d.P, d.K, d.L, d.G, d.C, slices, NT);
+  const SmemLayout2 &lay = layf.r;
+  float *s_w = reinterpret_cast<float *>(smem + lay.w);
+  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
+  uint4 *s_off = reinterpret_cast<uint4 *>(smem + lay.off);
+  float4 *s_bw = reinterpret_cast<float4 *>(smem + lay.bw);
+  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  int *s_list = reinterpret_cast<int *>(smem + lay.list);
+  int *s_tab = reinterpret_cast<int *>(smem + lay.tab);
+  float *s_red = reinterpret_cast<float *>(smem + lay.red);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + lay.bar);
+  int *s_nvalid = reinterpret_cast<int *>(bar + 1);
+  float *s_la = reinterpret_cast<float *>(smem + layf.la);
+  float *s_kp = reinterpret_cast<float *>(smem + layf.kp);
+  float *s_gred = reinterpret_cast<float *>(smem + layf.red);
+  float *s_inv = reinterpret_cast<float *>(smem + layf.inv);
+
+  const int tid = threadIdx.x;
+  const int anchor = blockIdx.x;  // b * A + a
+  const int b = anchor / d.A;
+  const int PK = d.P * d.K, LP = d.L * d.P, lpg = LP * d.G, n_el = d.K * lpg;
+#ifdef DFA_PHASE_TIMING
+  constexpr int NW = NT / 32;
+  const int lane = tid & 31, warp = tid >> 5;
+#endif
+  DFA_STAMP(0);
+
+  // The logits are the long pole of the prologue: start their TMA bulk copies first (camera part or
+  // the full block straight into the weight buffer, anchor part beside it) and compute key points,
+  // projections and the sample mask while they are in flight.
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+    if (fa.logits_k) {
+      mbar_expect_tx(bar, 4u * (n_el + lpg));
+      tma_bulk_g2s(s_w, fa.logits_k + static_cast<size_t>(b) * n_el, 4u * n_el, bar);
+      tma_bulk_g2s(s_la, fa.logits_a + static_cast<size_t>(anchor) * lpg, 4u * lpg, bar);
+    } else {
+      mbar_expect_tx(bar, 4u * n_el);
+      tma_bulk_g2s(s_w, fa.logits_a + static_cast<size_t>(anchor) * n_el, 4u * n_el, bar);
+    }
+  }
+  for (int i = tid; i < d.K * d.L; i += NT) {
+    s_tab[3 * i] = __ldg(shape + 2 * i);
+    s_tab[3 * i + 1] = __ldg(shape + 2 * i + 1);
+    s_tab[3 * i + 2] = __ldg(start + i);
+  }
+  // ---- key points, then their projections ---------------------------------------------------------
+  for (int p = tid; p < d.P; p += NT)
+    key_point(fa.anchor + static_cast<size_t>(anchor) * 11, fa.fix_scale, fa.num_fix,
+              fa.off_logits ? fa.off_logits + static_cast<size_t>(anchor) * (d.P - fa.num_fix) * 3 : nullptr,
+              p, s_kp[3 * p], s_kp[3 * p + 1], s_kp[3 * p + 2]);
+  __syncthreads();
+  DFA_STAMP(1);
+  for (int s = tid; s < PK; s += NT) {
+    const int p = s / d.K, k = s - p * d.K;
+    float px, py;
+    project_point(fa.proj + (static_cast<size_t>(b) * d.K + k) * 16,
+                  fa.wh ? fa.wh + (b * d.K + k) * 2 : nullptr, s_kp[3 * p], s_kp[3 * p + 1], s_kp[3 * p + 2],
+                  px, py);
+    s_loc[2 * s] = px, s_loc[2 * s + 1] = py;
+    if (fa.loc_out) {
+      fa.loc_out[(static_cast<size_t>(anchor) * PK + s) * 2] = px;
+      fa.loc_out[(static_cast<size_t>(anchor) * PK + s) * 2 + 1] = py;
+    }
+  }
+  DFA_STAMP(2);
+  // ---- compaction of the samples that pass the (0,1) test -------------------------------------------
+  __syncthreads();  // s_loc complete (and the mbarrier initialised for every waiter)
+  if (tid < 32) {
+    int n = 0;
+    for (int base = 0; base < PK; base += 32) {
+      const int s = base + tid;
+      bool v = false;
+      if (s < PK) v = sample_valid(s_loc[2 * s], s_loc[2 * s + 1]);
+      const unsigned m = __ballot_sync(0xffffffffu, v);
+      if (v) s_list[n + __popc(m & ((1u << tid) - 1u))] = s;
+      n += __popc(m);
+    }
+    if (tid == 0) *s_nvalid = n;
+  }
+  // ---- softmax numerators of the attention logits, natural (k,l,p,g) order ------------------------
+  // element e = i * NT + tid: its group is tid % G for every i (G divides NT), so a thread reduces
+  // its own elements first and the groups are combined once.
+  mbar_wait(bar, 0);
+  DFA_STAMP(3);
+  {
+    const bool split = fa.logits_k != nullptr;
+    float mx = -INFINITY;
+    int ia = tid % lpg;
+    for (int e = tid; e < n_el; e += NT) {
+      float v = s_w[e];
+      if (split) {
+        v += s_la[ia];
+        ia += NT;
+        while (ia >= lpg) ia -= lpg;
+        s_w[e] = v;
+      }
+      mx = fmaxf(mx, v);
+    }
+    mx = group_reduce<NT>(mx, s_gred, tid, d.G, true);
+    float sum = 0.f;
+    int e = tid;
+    for (; e + 3 * NT < n_el; e += 4 * NT) {  // four independent exponentials in flight
+      const float v0 = expf(s_w[e] - mx), v1 = expf(s_w[e + NT] - mx), v2 = expf(s_w[e + 2 * NT] - mx),
+                  v3 = expf(s_w[e + 3 * NT] - mx);
+      s_w[e] = v0, s_w[e + NT] = v1, s_w[e + 2 * NT] = v2, s_w[e + 3 * NT] = v3;
+      sum += (v0 + v1) + (v2 + v3);
+    }
+    for (; e < n_el; e += NT) {
+      const float v = expf(s_w[e] - mx);
+      s_w[e] = v;
+      sum += v;
+    }
+    sum = group_reduce<NT>(sum, s_gred, tid, d.G, false);
+    if (tid < d.G) s_inv[tid] = 1.f / sum;
+  }
+  DFA_STAMP(4);
+  __syncthreads();
+  const int nv = *s_nvalid;
+  const int ntaps = nv * d.L;
+  const int step = slices;
+  const int ntaps_pad = (ntaps + step - 1) / step * step;
+  for (int t = tid; t < ntaps_pad; t += NT) {
+    const int tt = t < ntaps ? t : 0;
+    const int l = tt / nv, i = tt - l * nv;
+    const int s = s_list[i];
+    const int p = s / d.K, k = s - p * d.K;
+    const int kl = k * d.L + l;
+    TapGeom gm;
+    tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], s_tab[3 * kl], s_tab[3 * kl + 1], s_tab[3 * kl + 2], gm);
+    const int safe = gm.row[0] >= 0 ? gm.row[0] : gm.row[1] >= 0 ? gm.row[1]
+                   : gm.row[2] >= 0 ? gm.row[2] : gm.row[3];
+    const float live = t < ntaps ? 1.f : 0.f;
+    const uint32_t rb = static_cast<uint32_t>(d.C) * sizeof(T);
+    uint4 off;
+    float4 bw;
+    off.x = (gm.row[0] >= 0 ? gm.row[0] : safe) * rb, bw.x = gm.row[0] >= 0 ? live * gm.hh * gm.hw : 0.f;
+    off.y = (gm.row[1] >= 0 ? gm.row[1] : safe) * rb, bw.y = gm.row[1] >= 0 ? live * gm.hh * gm.lw : 0.f;
+    off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, bw.z = gm.row[2] >= 0 ? live * gm.lh * gm.hw : 0.f;
+    off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, bw.w = gm.row[3] >= 0 ? live * gm.lh * gm.lw : 0.f;
+    s_off[t] = off, s_bw[t] = bw, s_widx[t] = ((k * d.L + l) * d.P + p) * d.G;  // (k,l,p,g) order
+  }
+  __syncthreads();
+  DFA_STAMP(5);
+
+  const int slice = tid >> vpr_log2, v = tid & (vpr - 1);
+  const int ch = v * VEC;
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+  if (slice < slices) {
+    const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
+                              static_cast<size_t>(b) * d.num_feat * d.C * sizeof(T);
+    const uint32_t lane_off = static_cast<uint32_t>(ch) * sizeof(T);
+    const float *s_wg = s_w + ch / (d.C / d.G);
+    for (int t = slice; t < ntaps_pad; t += step) {
+      typename FeatVec<T>::raw_t val[4];
+      const uint4 off = s_off[t];
+      val[0] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.x + lane_off)));
+      val[1] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.y + lane_off)));
+      val[2] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.z + lane_off)));
+      val[3] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off.w + lane_off)));
+      const float4 bw = s_bw[t];
+      const float wgt = s_wg[s_widx[t]];
+      FeatVec<T>::fma(acc, bw.x * wgt, val[0]);
+      FeatVec<T>::fma(acc, bw.y * wgt, val[1]);
+      FeatVec<T>::fma(acc, bw.z * wgt, val[2]);
+      FeatVec<T>::fma(acc, bw.w * wgt, val[3]);
+    }
+    float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
+#pragma unroll
+    for (int c = 0; c < VEC / 4; ++c)
+      r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+  }
+  DFA_STAMP(6);
+  __syncthreads();
+  const int cpg = d.C / d.G;
+  for (int c = tid; c < d.C; c += NT) {
+    float sum = 0.f;
+    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
+    out[static_cast<size_t>(anchor) * d.C + c] = sum * s_inv[c / cpg];  // the softmax denominator, once
+  }
+  DFA_STAMP(7);
+}
+
 // ------------------------------------------------------------------------------------------
 // forward with row merging and a balanced gather (the default for SimPB's shapes)
 // ------------------------------------------------------------------------------------------
@@ -302,18 +548,6 @@ __global__ void __launch_bounds__(NT, MINB)
 //                      output row is written once.
 //
 // Merge and summation order are fixed, so results are bitwise reproducible.
-#ifdef DFA_PHASE_TIMING
-// Tool-only build (tools/phase_timing.py): per-warp clock64() stamps at the phase boundaries of the
-// merging forward kernel, written to a caller-provided buffer [anchor][warp][8].
-__device__ long long *g_phase_buf = nullptr;
-#define DFA_STAMP(i)                                                                      \
-  do {                                                                                    \
-    if (g_phase_buf && lane == 0)                                                         \
-      g_phase_buf[(static_cast<size_t>(blockIdx.x) * NW + warp) * 8 + (i)] = clock64();   \
-  } while (0)
-#else
-#define DFA_STAMP(i) do {} while (0)
-#endif
 
 // NW: warps per CTA.  U: rows in flight per lane.
 template <typename T, int VPL, int G, int NW, int U, bool TMA, int MINB>
@@ -891,6 +1125,47 @@ int dfa_forward(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_s
     return forward_typed<__nv_bfloat16>(mc_ms_feat, spatial_shape, scale_start_index,
                                         sampling_location, weights, output, d, st);
   }
+  return DFA_ERR_BAD_DTYPE;
+}
+
+int dfa_forward_fused(const void *mc_ms_feat, int feat_dtype, const int32_t *spatial_shape,
+                      const int32_t *scale_start_index, const float *anchor, const float *fix_scale,
+                      int num_fix, const float *learnable_logits, const float *projection_mat,
+                      const float *image_wh, const float *logits_anchor, const float *logits_cam,
+                      float *output, float *sampling_location_out, const dfa_dims *dims, void *stream) {
+  if (!mc_ms_feat || !spatial_shape || !scale_start_index || !anchor || !fix_scale || !projection_mat ||
+      !logits_anchor || !output)
+    return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  if (num_fix < 0 || num_fix > d.P) return DFA_ERR_BAD_DIMS;
+  if (num_fix < d.P && !learnable_logits) return DFA_ERR_NULL_POINTER;
+  constexpr int NT = 256;
+  if (d.G > 32 || (d.G & (d.G - 1)) != 0) return DFA_ERR_UNSUPPORTED;  // group reductions by shuffles
+  {  // the logits are staged by TMA bulk copies: 16-byte sized / aligned blocks, mbarrier-countable
+    const long long lpg = static_cast<long long>(d.L) * d.P * d.G;
+    if ((4 * lpg) % 16 != 0 || 4 * lpg * (d.K + 1) >= (1ll << 20) || !aligned(logits_anchor, 16) ||
+        (logits_cam && !aligned(logits_cam, 16)))
+      return DFA_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const FusedArgs fa{anchor, fix_scale, learnable_logits, projection_mat, image_wh, logits_anchor, logits_cam,
+                     sampling_location_out, num_fix};
+  auto launch = [&](auto tag) -> int {
+    using T = decltype(tag);
+    const int vpr = rows_vpr<T>(d, mc_ms_feat, NT);
+    if (!vpr) return DFA_ERR_UNSUPPORTED;
+    int vpr_log2 = 0;
+    while ((1 << vpr_log2) < vpr) ++vpr_log2;
+    auto kern = dfa_fwd_fused_kernel<T, NT, 6>;
+    const SmemLayoutF lay = smem_layout_fused(d.P, d.K, d.L, d.G, d.C, NT / vpr, NT);
+    if (int rc = set_smem(kern, lay.total)) return rc;
+    kern<<<d.bs * d.A, NT, lay.total, st>>>(static_cast<const T *>(mc_ms_feat), spatial_shape,
+                                            scale_start_index, fa, output, d, vpr_log2);
+    return static_cast<int>(cudaGetLastError());
+  };
+  if (feat_dtype == DFA_F32) return launch(float{});
+  if (feat_dtype == DFA_BF16) return launch(__nv_bfloat16{});
   return DFA_ERR_BAD_DTYPE;
 }
 

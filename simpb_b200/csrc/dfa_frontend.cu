@@ -53,31 +53,14 @@ __global__ void __launch_bounds__(256)
   const int p = static_cast<int>(i % P);
   const long long ba = i / P;
   const int b = static_cast<int>(ba / A);
-  const float *an = anchor + ba * 11;
-  const float sx = expf(an[3]), sy = expf(an[4]), sz = expf(an[5]);  // W, L, H
-  float ox, oy, oz;
-  if (p < num_fix) {
-    ox = fix_scale[3 * p], oy = fix_scale[3 * p + 1], oz = fix_scale[3 * p + 2];
-  } else {
-    const float *lg = logits + ba * (P - num_fix) * 3 + (p - num_fix) * 3;
-    ox = 1.f / (1.f + expf(-lg[0])) - 0.5f;
-    oy = 1.f / (1.f + expf(-lg[1])) - 0.5f;
-    oz = 1.f / (1.f + expf(-lg[2])) - 0.5f;
-  }
-  ox *= sx, oy *= sy, oz *= sz;
-  const float sn = an[6], cs = an[7];
-  const float x = fmaf(cs, ox, -sn * oy) + an[0];
-  const float y = fmaf(sn, ox, cs * oy) + an[1];
-  const float z = oz + an[2];
+  float x, y, z;
+  key_point(anchor + ba * 11, fix_scale, num_fix,
+            logits ? logits + ba * (P - num_fix) * 3 : nullptr, p, x, y, z);
   if (kp_out) kp_out[3 * i] = x, kp_out[3 * i + 1] = y, kp_out[3 * i + 2] = z;
   for (int k = 0; k < K; ++k) {
-    const float *m = proj + (static_cast<size_t>(b) * K + k) * 16;
-    const float u = fmaf(m[2], z, fmaf(m[1], y, m[0] * x)) + m[3];
-    const float v = fmaf(m[6], z, fmaf(m[5], y, m[4] * x)) + m[7];
-    const float dpt = fmaf(m[10], z, fmaf(m[9], y, m[8] * x)) + m[11];
-    const float den = fmaxf(dpt, 1e-5f);
-    float px = u / den, py = v / den;
-    if (wh) px /= wh[(b * K + k) * 2], py /= wh[(b * K + k) * 2 + 1];
+    float px, py;
+    project_point(proj + (static_cast<size_t>(b) * K + k) * 16, wh ? wh + (b * K + k) * 2 : nullptr, x, y, z,
+                  px, py);
     float *o = loc_out + (static_cast<size_t>(i) * K + k) * 2;
     o[0] = px, o[1] = py;
   }
@@ -158,31 +141,6 @@ __global__ void __launch_bounds__(128)
 // K*L*P entries of each (b, a, g).  keep [bs, A, K, P] (uint8, may be NULL) is the attn-drop keep
 // mask of models/blocks.py:188-195 and `scale` its 1/(1-p).  One CTA per anchor; the anchor's
 // logits are staged in shared memory once.  Thread t owns group t % G (G divides the block).
-// Reduction over the threads that own the same group (tid % G, G a power of two <= 32 here): xor
-// shuffles inside the warp, then one shared-memory row per warp.
-template <int NT>
-__device__ __forceinline__ float group_reduce(float v, float *s_red, int tid, int G, bool is_max) {
-  if (G <= 32 && (G & (G - 1)) == 0) {
-    for (int m = G; m < 32; m <<= 1) {
-      const float o = __shfl_xor_sync(0xffffffffu, v, m);
-      v = is_max ? fmaxf(v, o) : v + o;
-    }
-    const int lane = tid & 31, warp = tid >> 5;
-    if (lane < G) s_red[warp * G + lane] = v;
-    __syncthreads();
-    float r = s_red[lane % G];
-    for (int w = 1; w < NT / 32; ++w) r = is_max ? fmaxf(r, s_red[w * G + lane % G]) : r + s_red[w * G + lane % G];
-    __syncthreads();
-    return r;
-  }
-  s_red[tid] = v;
-  __syncthreads();
-  float r = s_red[tid % G];
-  for (int j = (tid % G) + G; j < NT; j += G) r = is_max ? fmaxf(r, s_red[j]) : r + s_red[j];
-  __syncthreads();
-  return r;
-}
-
 // `logits_cam` (may be NULL) is the camera part of split logits: weights_fc is linear, so
 // weights_fc(feature[b,a] + camera_embed[b,k]) = weights_fc(feature[b,a]) + W * camera_embed[b,k];
 // the module then runs the GEMM on [bs*A] and [bs*K] rows instead of [bs*A*K] and this kernel adds
@@ -328,35 +286,68 @@ __device__ __forceinline__ float4 quad_reduce(float4 v, float4 *s_red4, int tid,
   return r;
 }
 
-// numerators into s_x4, returns 1/sum for the thread's four groups
-template <int NT>
-__device__ __forceinline__ float4 softmax_stage4(float4 *s_x4, float4 *s_red4, const float4 *la,
-                                                 const float4 *lk, int tid, int K, int LP, int Q) {
-  const int q = tid % Q, r0 = tid / Q, rs = NT / Q;
-  float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-  for (int k = 0; k < K; ++k)
-    for (int r = r0; r < LP; r += rs) {
-      const int e = (k * LP + r) * Q + q;
-      float4 v;
-      if (lk) {
-        const float4 a = __ldg(la + r * Q + q), c = __ldg(lk + e);
-        v = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
-      } else {
-        v = __ldg(la + e);
-      }
-      s_x4[e] = v;
-      mx = make_float4(fmaxf(mx.x, v.x), fmaxf(mx.y, v.y), fmaxf(mx.z, v.z), fmaxf(mx.w, v.w));
+// The logits of one anchor are staged by TMA bulk copies (camera part or the full block straight into
+// the working buffer, anchor part beside it): one round trip instead of one per loop iteration.
+struct SoftmaxStage4 {
+  float4 *x4;     // N*Q working buffer
+  float4 *la4;    // LP*Q anchor part (split logits only)
+  uint64_t *bar;
+};
+__device__ __forceinline__ SoftmaxStage4 softmax_stage4_layout(float *after_tables_base, int N, int n_el,
+                                                               int lpg, float4 *x4) {
+  // tables (3*N bytes) sit at `after_tables_base`; the anchor part and the barrier follow, 16-byte aligned
+  unsigned char *p = reinterpret_cast<unsigned char *>(after_tables_base) + align_up(3u * N, 16);
+  SoftmaxStage4 st;
+  st.x4 = x4;
+  st.la4 = reinterpret_cast<float4 *>(p);
+  st.bar = reinterpret_cast<uint64_t *>(p + 4u * lpg);
+  (void)n_el;
+  return st;
+}
+__device__ __forceinline__ void softmax_issue4(const SoftmaxStage4 &st, const float *la_g, const float *lk_g,
+                                               int tid, int n_el, int lpg) {
+  if (tid == 0) {
+    mbar_init(st.bar, 1);
+    fence_mbar_init();
+    if (lk_g) {
+      mbar_expect_tx(st.bar, 4u * (n_el + lpg));
+      tma_bulk_g2s(st.x4, lk_g, 4u * n_el, st.bar);
+      tma_bulk_g2s(st.la4, la_g, 4u * lpg, st.bar);
+    } else {
+      mbar_expect_tx(st.bar, 4u * n_el);
+      tma_bulk_g2s(st.x4, la_g, 4u * n_el, st.bar);
     }
+  }
+}
+
+// numerators into st.x4, returns 1/sum for the thread's four groups.  Element e4 = i*NT + tid has
+// quad tid % Q for every i (Q divides NT).
+template <int NT>
+__device__ __forceinline__ float4 softmax_stage4(const SoftmaxStage4 &st, float4 *s_red4, bool split, int tid,
+                                                 int n4, int lp4, int Q) {
+  __syncthreads();  // barrier initialised (and the tables written) for every thread
+  mbar_wait(st.bar, 0);
+  float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  int ia = tid % lp4;
+  for (int e = tid; e < n4; e += NT) {
+    float4 v = st.x4[e];
+    if (split) {
+      const float4 a = st.la4[ia];
+      ia += NT;
+      while (ia >= lp4) ia -= lp4;
+      v = make_float4(a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w);
+      st.x4[e] = v;
+    }
+    mx = make_float4(fmaxf(mx.x, v.x), fmaxf(mx.y, v.y), fmaxf(mx.z, v.z), fmaxf(mx.w, v.w));
+  }
   mx = quad_reduce<NT>(mx, s_red4, tid, Q, true);
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < K; ++k)
-    for (int r = r0; r < LP; r += rs) {
-      const int e = (k * LP + r) * Q + q;
-      float4 v = s_x4[e];
-      v = make_float4(expf(v.x - mx.x), expf(v.y - mx.y), expf(v.z - mx.z), expf(v.w - mx.w));
-      s_x4[e] = v;
-      sum.x += v.x, sum.y += v.y, sum.z += v.z, sum.w += v.w;
-    }
+  for (int e = tid; e < n4; e += NT) {
+    float4 v = st.x4[e];
+    v = make_float4(expf(v.x - mx.x), expf(v.y - mx.y), expf(v.z - mx.z), expf(v.w - mx.w));
+    st.x4[e] = v;
+    sum.x += v.x, sum.y += v.y, sum.z += v.z, sum.w += v.w;
+  }
   sum = quad_reduce<NT>(sum, s_red4, tid, Q, false);
   return make_float4(1.f / sum.x, 1.f / sum.y, 1.f / sum.z, 1.f / sum.w);
 }
@@ -375,9 +366,10 @@ __global__ void __launch_bounds__(NT)
   const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
   const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * LP * G : logits + base;
   const float *lk = logits_cam ? logits_cam + static_cast<size_t>(blockIdx.x / A) * n_el : nullptr;
+  const SoftmaxStage4 st = softmax_stage4_layout(s_x + n_el, N, n_el, LP * G, s_x4);
+  softmax_issue4(st, la, lk, tid, n_el, LP * G);
   softmax_tables<NT>(tb, keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr, tid, K, L, P);
-  const float4 inv = softmax_stage4<NT>(s_x4, s_red4, reinterpret_cast<const float4 *>(la),
-                                        reinterpret_cast<const float4 *>(lk), tid, K, LP, Q);
+  const float4 inv = softmax_stage4<NT>(st, s_red4, lk != nullptr, tid, N * Q, LP * Q, Q);
   const int q = tid % Q, r0 = tid / Q, rs = NT / Q;
   const float on = keep ? scale : 1.f;
   float4 *w4 = reinterpret_cast<float4 *>(w + base);
@@ -406,9 +398,10 @@ __global__ void __launch_bounds__(NT)
   const size_t base = static_cast<size_t>(blockIdx.x) * n_el;
   const float *la = logits_cam ? logits + static_cast<size_t>(blockIdx.x) * LP * G : logits + base;
   const float *lk = logits_cam ? logits_cam + static_cast<size_t>(blockIdx.x / A) * n_el : nullptr;
+  const SoftmaxStage4 st = softmax_stage4_layout(s_x + 2 * n_el, N, n_el, LP * G, s_x4);
+  softmax_issue4(st, la, lk, tid, n_el, LP * G);
   softmax_tables<NT>(tb, keep ? keep + static_cast<size_t>(blockIdx.x) * K * P : nullptr, tid, K, L, P);
-  const float4 inv = softmax_stage4<NT>(s_x4, s_red4, reinterpret_cast<const float4 *>(la),
-                                        reinterpret_cast<const float4 *>(lk), tid, K, LP, Q);
+  const float4 inv = softmax_stage4<NT>(st, s_red4, lk != nullptr, tid, N * Q, LP * Q, Q);
   const int q = tid % Q, r0 = tid / Q, rs = NT / Q;
   const float on = keep ? scale : 1.f;
   const float4 *gw4 = reinterpret_cast<const float4 *>(grad_w + base);
@@ -528,7 +521,9 @@ int softmax_check(long long n_anchors, int K, int L, int P, int G, long long sme
   if (n_anchors <= 0 || K <= 0 || L <= 0 || P <= 0 || G <= 0) return DFA_ERR_BAD_DIMS;
   if (n_anchors >= (1ll << 31) || SOFTMAX_NT % G != 0) return DFA_ERR_UNSUPPORTED;
   if (static_cast<long long>(K) * L * P >= 65536) return DFA_ERR_UNSUPPORTED;  // 16-bit row table
-  const long long bytes = 4ll * K * L * P * G * smem_floats + 3ll * K * L * P + 16;
+  // working buffers + row tables + (vector kernels) the TMA-staged anchor part and its mbarrier
+  const long long bytes = 4ll * K * L * P * G * smem_floats + 3ll * K * L * P + 16 + 4ll * L * P * G + 32;
+  if (4ll * (K + 1) * L * P * G >= (1ll << 20)) return DFA_ERR_UNSUPPORTED;
   if (bytes > 200ll * 1024) return DFA_ERR_UNSUPPORTED;
   *smem = static_cast<uint32_t>(bytes);
   return 0;

@@ -207,6 +207,51 @@ def test_module_backward_matches_torch_autograd_of_the_reference_path(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_inference_kernel_matches_the_three_kernel_path(dtype):
+    """dfa_forward_fused (key points + projection + softmax + gather in one launch) against the
+    separate kernels at the released config: identical sampling locations, outputs to rounding; and
+    the module takes the fused path exactly when no gradient is needed."""
+    from simpb_b200 import blocks, cabi, feature_maps_format, synthetic
+    torch.manual_seed(0)
+    m = blocks.DeformableFeatureAggregation(
+        embed_dims=256, num_groups=8, num_levels=4, num_cams=6, attn_drop=0.15, use_camera_embed=True,
+        residual_mode="cat", kps_generator=dict(type="SparseBox3DKeyPointsGenerator", num_learnable_pts=6,
+                                                fix_scale=synthetic.FIX_SCALE)).cuda().eval()
+    d = synthetic.module_inputs_rig(bs=2, A=300, levels=((16, 44), (8, 22), (4, 11), (2, 6)), seed=11)
+    g = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+    fm = feature_maps_format([x.cuda() for x in d["feature_maps"]], dtype=dtype)
+    metas = dict(projection_mat=g["projection_mat"], image_wh=g["image_wh"])
+    args = (g["instance_feature"], g["anchor"], g["anchor_embed"])
+    with torch.no_grad():
+        loc, w = m.sampling_and_weights(*args, metas)
+        want = cabi.forward(fm[0], fm[1].int(), fm[2].int(), loc, w)
+        got = m.fused_features(*args, fm, metas)
+        assert got is not None
+        assert_close(got, want, 2e-6, "fused features")
+        gen = m.kps_generator
+        cam = m.camera_encoder(metas["projection_mat"][:, :, :3].reshape(2, 6, -1))
+        out2, loc2 = cabi.forward_fused(
+            fm[0], fm[1].int(), fm[2].int(), g["anchor"], gen.fix_scale, gen.offset_logits(g["instance_feature"]),
+            g["projection_mat"], g["image_wh"], m.weights_fc(g["instance_feature"] + g["anchor_embed"]),
+            torch.nn.functional.linear(cam, m.weights_fc.weight).contiguous(), (2, 300, 6, 4, 13, 8),
+            want_locations=True)
+        assert torch.equal(loc2, loc)                       # same device code: bit-identical locations
+        assert torch.equal(out2, got)
+        y_fused = m(*args, fm, metas)                       # eval + no_grad: fused path
+    y_sep = m(*args, fm, metas)                             # parameters require grad: separate kernels
+    assert_close(y_fused, y_sep, 2e-6, "module output, fused vs separate")
+    # full (unsplit) logits through the same entry point
+    m2 = blocks.DeformableFeatureAggregation(embed_dims=256, num_groups=8, num_levels=4, num_cams=6,
+                                             kps_generator=dict(type="SparseBox3DKeyPointsGenerator",
+                                                                fix_scale=synthetic.FIX_SCALE)).cuda().eval()
+    with torch.no_grad():
+        loc, w = m2.sampling_and_weights(*args, metas)
+        want = cabi.forward(fm[0], fm[1].int(), fm[2].int(), loc, w)
+        assert_close(m2.fused_features(*args, fm, metas), want, 2e-6, "fused features, no camera embedding")
+
+
+@pytest.mark.gpu
 def test_softmax_weights_kernel_r50_shape_vs_torch():
     from simpb_b200 import cabi
     gen = torch.Generator().manual_seed(1)
