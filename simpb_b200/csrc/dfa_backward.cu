@@ -704,7 +704,6 @@ int backward_typed(const void *feat, const int *shape, const int *start, const f
       switch (variant) {
         case 11: return BWDV(4, 2, 10);
         case 12: return BWDV(8, 4, 4);
-        case 13: return BWDV(8, 2, 5);
         default: return BWDV(4, 4, 8);
       }
 #undef BWDV

@@ -12,6 +12,19 @@
 
 namespace {
 
+#ifdef DFA_PHASE_TIMING
+// Tool-only build (tools/phase_timing.py): per-warp clock64() stamps at the phase boundaries of the
+// merging forward kernel, written to a caller-provided buffer [anchor][warp][8].
+__device__ long long *g_phase_buf = nullptr;
+#define DFA_STAMP(i)                                                                      \
+  do {                                                                                    \
+    if (g_phase_buf && lane == 0)                                                         \
+      g_phase_buf[(static_cast<size_t>(blockIdx.x) * NW + warp) * 8 + (i)] = clock64();   \
+  } while (0)
+#else
+#define DFA_STAMP(i) do {} while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
@@ -167,6 +180,11 @@ __global__ void __launch_bounds__(NT, MINB)
   int *s_nvalid = reinterpret_cast<int *>(bars + 2);
 
   const int tid = threadIdx.x;
+#ifdef DFA_PHASE_TIMING
+  constexpr int NW = NT / 32;
+  const int lane = tid & 31, warp = tid >> 5;
+#endif
+  DFA_STAMP(0);
   const int anchor = blockIdx.x;  // b * A + a
   const int b = anchor / d.A;
   const int PK = d.P * d.K, wcount = PK * d.L * d.G;
@@ -180,6 +198,7 @@ __global__ void __launch_bounds__(NT, MINB)
   const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
                                         weights + static_cast<size_t>(anchor) * wcount, s_w,
                                         s_loc, s_list, bars, s_nvalid, PK, wcount);
+  DFA_STAMP(1);
   const int ntaps = nv * d.L;
   const int step = slices * U;
   const int ntaps_pad = (ntaps + step - 1) / step * step;
@@ -218,8 +237,10 @@ __global__ void __launch_bounds__(NT, MINB)
       if (gm.row[3] >= 0) tma_prefetch_l2(fr + off.w, rb);
     }
   }
+  DFA_STAMP(2);
   __syncthreads();
   if (TMA) mbar_wait(&bars[1], 0);  // weights have landed
+  DFA_STAMP(3);
 
   const int slice = tid >> vpr_log2, v = tid & (vpr - 1);
   const int ch = v * VEC;
@@ -261,27 +282,17 @@ __global__ void __launch_bounds__(NT, MINB)
     for (int c = 0; c < VEC / 4; ++c)
       r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
   }
+  DFA_STAMP(4);
   __syncthreads();
   for (int c = tid; c < d.C; c += NT) {
     float sum = 0.f;
     for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
     out[static_cast<size_t>(anchor) * d.C + c] = sum;
   }
+  DFA_STAMP(5);
 }
 
 
-#ifdef DFA_PHASE_TIMING
-// Tool-only build (tools/phase_timing.py): per-warp clock64() stamps at the phase boundaries of the
-// merging forward kernel, written to a caller-provided buffer [anchor][warp][8].
-__device__ long long *g_phase_buf = nullptr;
-#define DFA_STAMP(i)                                                                      \
-  do {                                                                                    \
-    if (g_phase_buf && lane == 0)                                                         \
-      g_phase_buf[(static_cast<size_t>(blockIdx.x) * NW + warp) * 8 + (i)] = clock64();   \
-  } while (0)
-#else
-#define DFA_STAMP(i) do {} while (0)
-#endif
 
 // ------------------------------------------------------------------------------------------
 // fused module forward: key points + projection + softmax of the attention logits + gather
@@ -1011,8 +1022,9 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
                   const float *w, float *out, const Dims &d, cudaStream_t st) {
   // DFA_FWD_VARIANT (tuning knob): 1..4 = row-sliced kernel with (threads, taps in flight) =
   // (256,1) (256,2) (512,1) (512,2) — 1 is the default, the fastest measured on B200 at SimPB's
-  // shapes; 10.. = row-merging kernel (fewer DRAM bytes and L1 wavefronts, longer dependent chain
-  // per warp: within 5-25 % of the default); 0 = one-warp-per-group kernel.
+  // shapes (192- and 128-thread CTAs and a 32-register build were tried and lost 20-40 %);
+  // 10..12 = row-merging kernel (fewer DRAM bytes and L1 wavefronts, longer dependent chain per
+  // warp: within 5-25 % of the default); 0 = one-warp-per-group kernel.
   // A variant whose shape constraints are not met falls through to the next family.
   const int variant = env_int("DFA_FWD_VARIANT", 1);
   if (variant >= 10) {  // merging kernel: (warps, rows in flight, CTAs per SM) per variant
@@ -1025,12 +1037,7 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
 #define WARPV(NW, U, MINB) (vpl == 2 ? WARPK(2, NW, U, MINB) : WARPK(1, NW, U, MINB))
       switch (variant) {
         case 11: return WARPV(4, 4, 8);
-        case 12: return WARPV(4, 4, 9);
-        case 13: return WARPV(4, 2, 12);
-        case 14: return WARPV(8, 4, 5);
-        case 15: return WARPV(8, 4, 4);
-        case 16: return WARPV(8, 2, 6);
-        case 17: return WARPV(2, 4, 18);
+        case 12: return WARPV(8, 4, 4);
         default: return WARPV(4, 4, 10);
       }
 #undef WARPV
@@ -1039,7 +1046,7 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   }
   const int rvariant = variant >= 10 ? 1 : variant;
   if (rvariant >= 1) {
-    const int nt = rvariant == 5 ? 192 : rvariant == 6 ? 128 : rvariant >= 3 ? 512 : 256;
+    const int nt = rvariant >= 3 ? 512 : 256;
     const int vpr = rows_vpr<T>(d, feat, nt);
     if (vpr) {
       const bool tma = tma_ok(d, loc, w);
@@ -1052,8 +1059,6 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
         case 1: return ROWS(1, 256, 6);
         case 2: return ROWS(2, 256, 4);
         case 3: return ROWS(1, 512, 3);
-        case 5: return ROWS(1, 192, 8);
-        case 6: return ROWS(1, 128, 12);
         default: return ROWS(2, 512, 2);
       }
 #undef ROWS

@@ -137,7 +137,7 @@ def test_r50_shape_rig_vs_oracle():
     check_case(synthetic.rig_op_inputs(bs=2, seed=3))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14, 15, 16, 17])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 10, 11, 12])
 def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
     """DFA_FWD_VARIANT selects the forward kernel family / tuning point; all of them must agree
     with the oracle (fp32 and bf16 feature tables, sparse rig and dense uniform locations)."""
@@ -158,7 +158,7 @@ def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
             assert_close(out, ref, RTOL_F32, "variant %d %s" % (variant, dtype))
 
 
-@pytest.mark.parametrize("variant", [0, 10, 11, 12, 13])
+@pytest.mark.parametrize("variant", [0, 10, 11, 12])
 def test_every_backward_kernel_variant_vs_oracle(variant, monkeypatch):
     """DFA_BWD_VARIANT: row-merging backward (tuning points) and the one-warp-per-group kernel, both
     buffer contracts, fp32 and bf16 feature tables, sparse / dense / many-sample anchors."""

@@ -56,8 +56,12 @@ for i in range(3):   # the last launch (cold inputs: 3 sets rotate) is the one a
     assert rc == 0, rc
 torch.cuda.synchronize()
 t = buf.cpu().double()
-names = ["0 start", "1 loc landed / tables", "2 compaction+weights issued", "3 barrier A", "4 merge done",
-         "5 barrier B", "6 gather done", "7 end"]
+if a.variant < 10:     # row-sliced kernel: its own stamp meanings
+    names = ["0 start", "1 operands staged + compaction", "2 tap records", "3 barrier + weights landed",
+             "4 gather done", "5 end", "-", "-"]
+else:
+    names = ["0 start", "1 loc landed / tables", "2 compaction+weights issued", "3 barrier A", "4 merge done",
+             "5 barrier B", "6 gather done", "7 end"]
 t0 = t[:, :, 0].min(dim=1, keepdim=True).values          # CTA start
 print("variant", a.variant, "batch", a.batch, "anchors", n_anchor)
 print("phase stamps relative to CTA start, cycles: median / p90 / max over (anchor, warp)")
@@ -66,7 +70,8 @@ for i in range(1, 8):
     x = x[t[:, :, i].flatten() > 0]
     if x.numel():
         print("  %-30s %8.0f %8.0f %8.0f" % (names[i], x.median(), x.quantile(0.9), x.max()))
-life = (t[:, :, 7].max(dim=1).values - t0[:, 0])
+last = 5 if a.variant < 10 else 7
+life = (t[:, :, last].max(dim=1).values - t0[:, 0])
 print("CTA lifetime: median %.0f p90 %.0f max %.0f cycles" % (life.median(), life.quantile(0.9), life.max()))
-span = t[:, :, 7].max() - t[:, :, 0][t[:, :, 0] > 0].min()
+span = t[:, :, last].max() - t[:, :, 0][t[:, :, 0] > 0].min()
 print("(clock64 is per SM; first start to last end across SMs is only indicative: %.0f cycles)" % span)

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from simpb_b200 import cabi, synthetic  # noqa: E402
 import bench  # noqa: E402
 
-variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,5,6").split(",")]
+variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,2,10,11,12").split(",")]
 cases = [("rig", 1, "f32"), ("uniform", 1, "f32"), ("rig", 8, "f32"), ("rig", 1, "bf16"), ("rig", 8, "bf16")]
 for inputs, batch, dt in cases:
     maker = synthetic.rig_op_inputs if inputs == "rig" else synthetic.op_inputs_uniform
