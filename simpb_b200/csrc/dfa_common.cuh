@@ -189,22 +189,33 @@ struct TapB {  // backward record, one per tap
 };
 
 // Stage the anchor's locations and weights, compact valid samples.  Returns n_valid.
+// First thing a CTA does: thread 0 starts the two TMA bulk copies of the anchor's operands, so that
+// nothing else (level-table loads, index arithmetic) sits in front of that round trip.
+template <bool TMA>
+__device__ __forceinline__ void stage_issue(const float *__restrict__ loc_g, const float *__restrict__ w_g,
+                                            float *s_w, float *s_loc, uint64_t *bars, int PK, int wcount) {
+  if (TMA && threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&bars[0], 8u * PK);
+    tma_bulk_g2s(s_loc, loc_g, 8u * PK, &bars[0]);
+    mbar_expect_tx(&bars[1], 4u * wcount);
+    tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
+  }
+}
+
+// Wait for the locations (plain loads of both operands when TMA is off), compact valid samples.
+// `issued`: stage_issue() already ran.  Returns n_valid.
 template <bool TMA>
 __device__ __forceinline__ int stage_and_compact(const float *__restrict__ loc_g,
                                                  const float *__restrict__ w_g, float *s_w,
                                                  float *s_loc, int *s_list, uint64_t *bars,
-                                                 int *s_nvalid, int PK, int wcount) {
+                                                 int *s_nvalid, int PK, int wcount,
+                                                 bool issued = false) {
   const int tid = threadIdx.x;
   if (TMA) {
-    if (tid == 0) {
-      mbar_init(&bars[0], 1);
-      mbar_init(&bars[1], 1);
-      fence_mbar_init();
-      mbar_expect_tx(&bars[0], 8u * PK);
-      tma_bulk_g2s(s_loc, loc_g, 8u * PK, &bars[0]);
-      mbar_expect_tx(&bars[1], 4u * wcount);
-      tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
-    }
+    if (!issued) stage_issue<TMA>(loc_g, w_g, s_w, s_loc, bars, PK, wcount);
     __syncthreads();  // barrier init visible to every waiter
     if (tid < 32) mbar_wait(&bars[0], 0);
   } else {

@@ -189,7 +189,11 @@ __global__ void __launch_bounds__(NT, MINB)
   const int b = anchor / d.A;
   const int PK = d.P * d.K, wcount = PK * d.L * d.G;
 
-  // level tables → shared memory while the TMA copies are in flight
+  // operands first (tried: plain loads for the locations, and weight lines of the valid samples only
+  // after the mask is known — both slower at this shape), then the level tables → shared memory
+  // while the TMA copies are in flight
+  stage_issue<TMA>(loc + static_cast<size_t>(anchor) * PK * 2, weights + static_cast<size_t>(anchor) * wcount,
+                   s_w, s_loc, bars, PK, wcount);
   for (int i = tid; i < d.K * d.L; i += NT) {
     s_tab[3 * i] = __ldg(shape + 2 * i);
     s_tab[3 * i + 1] = __ldg(shape + 2 * i + 1);
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(NT, MINB)
   }
   const int nv = stage_and_compact<TMA>(loc + static_cast<size_t>(anchor) * PK * 2,
                                         weights + static_cast<size_t>(anchor) * wcount, s_w,
-                                        s_loc, s_list, bars, s_nvalid, PK, wcount);
+                                        s_loc, s_list, bars, s_nvalid, PK, wcount, true);
   DFA_STAMP(1);
   const int ntaps = nv * d.L;
   const int step = slices * U;
