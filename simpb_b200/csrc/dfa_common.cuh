@@ -56,10 +56,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-// TMA bulk prefetch of `bytes` (multiple of 16) into L2: no registers, no shared memory.
-__device__ __forceinline__ void tma_prefetch_l2(const void *src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
                "f"(d)

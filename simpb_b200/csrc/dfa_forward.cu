@@ -157,7 +157,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int P, int K, int L, int G, 
   return s;
 }
 
-template <typename T, int U, bool TMA, int NT, int MINB, bool PF>
+template <typename T, int U, bool TMA, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
     dfa_fwd_rows_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
                         const int *__restrict__ start, const float *__restrict__ loc,
@@ -231,15 +231,6 @@ __global__ void __launch_bounds__(NT, MINB)
     off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, bw.z = gm.row[2] >= 0 ? live * gm.lh * gm.hw : 0.f;
     off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, bw.w = gm.row[3] >= 0 ? live * gm.lh * gm.lw : 0.f;
     s_off[t] = off, s_bw[t] = bw, s_widx[t] = (s * d.L + l) * d.G;
-    if (PF && t < ntaps) {
-      // start the rows' DRAM → L2 transfers now, long before the first register load needs them
-      const unsigned char *fr = reinterpret_cast<const unsigned char *>(feat) +
-                                static_cast<size_t>(b) * d.num_feat * rb;
-      if (gm.row[0] >= 0) tma_prefetch_l2(fr + off.x, rb);
-      if (gm.row[1] >= 0) tma_prefetch_l2(fr + off.y, rb);
-      if (gm.row[2] >= 0) tma_prefetch_l2(fr + off.z, rb);
-      if (gm.row[3] >= 0) tma_prefetch_l2(fr + off.w, rb);
-    }
   }
   DFA_STAMP(2);
   __syncthreads();
@@ -570,7 +561,7 @@ __global__ void __launch_bounds__(NW * 32, MINB)
     dfa_fwd_merge_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
                          const int *__restrict__ start, const float *__restrict__ loc,
                          const float *__restrict__ weights, float *__restrict__ out, Dims d,
-                         MergeLayout lay, int whole_weights, int prefetch) {
+                         MergeLayout lay, int whole_weights) {
   constexpr int VEC = FeatVec<T>::VEC;
   constexpr int NT = NW * 32;
   constexpr int GPV = G / VPL;  // groups covered by one 512-byte segment of the row
@@ -779,10 +770,6 @@ __global__ void __launch_bounds__(NW * 32, MINB)
       } else if (fresh) {
         s_table[h] = (static_cast<uint32_t>(row) << 6) | static_cast<uint32_t>(slot);
         my_rowoff[slot] = static_cast<uint32_t>(row) * rb;
-        if (prefetch == 1)  // start the row's DRAM -> L2 transfer now; the gather then runs at L2 latency
-          tma_prefetch_l2(fb - lane * 16 + static_cast<uint32_t>(row) * rb, rb);
-        else if (prefetch == 2)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(fb - lane * 16 + static_cast<uint32_t>(row) * rb));
 #pragma unroll
         for (int x = 0; x < G / 4; ++x)
           cp[x] = make_float4(cf[4 * x], cf[4 * x + 1], cf[4 * x + 2], cf[4 * x + 3]);
@@ -979,10 +966,10 @@ int launch_fwd_t(const void *feat, const int *shape, const int *start, const flo
     default: return CALL(1);                      \
   }
 
-template <typename T, int U, bool TMA, int NT, int MINB, bool PF>
+template <typename T, int U, bool TMA, int NT, int MINB>
 int launch_fwd_rows(const void *feat, const int *shape, const int *start, const float *loc,
                     const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
-  auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB, PF>;
+  auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB>;
   const int slices = NT / vpr;
   int vpr_log2 = 0;
   while ((1 << vpr_log2) < vpr) ++vpr_log2;
@@ -1015,9 +1002,8 @@ int launch_fwd_merge(const void *feat, const int *shape, const int *start, const
   // whole weights block at once instead of waiting for the sample mask first.
   const long long grid = static_cast<long long>(d.bs) * d.A;
   const int whole = env_int("DFA_FWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0);
-  const int prefetch = env_int("DFA_FWD_PREFETCH", 0);
   kern<<<d.bs * d.A, NW * 32, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
-                                              out, d, lay, whole, prefetch);
+                                              out, d, lay, whole);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1054,11 +1040,9 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
     const int vpr = rows_vpr<T>(d, feat, nt);
     if (vpr) {
       const bool tma = tma_ok(d, loc, w);
-      const bool pf = env_int("DFA_FWD_PREFETCH", 0) != 0;
-#define ROWS(U, NT, MINB)                                                                              \
-  (tma ? (pf ? launch_fwd_rows<T, U, true, NT, MINB, true>(feat, shape, start, loc, w, out, d, vpr, st)  \
-             : launch_fwd_rows<T, U, true, NT, MINB, false>(feat, shape, start, loc, w, out, d, vpr, st)) \
-       : launch_fwd_rows<T, U, false, NT, MINB, false>(feat, shape, start, loc, w, out, d, vpr, st))
+#define ROWS(U, NT, MINB)                                                                        \
+  (tma ? launch_fwd_rows<T, U, true, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st)        \
+       : launch_fwd_rows<T, U, false, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st))
       switch (rvariant) {
         case 1: return ROWS(1, 256, 6);
         case 2: return ROWS(2, 256, 4);

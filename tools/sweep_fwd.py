@@ -17,9 +17,8 @@ for inputs, batch, dt in cases:
     sets = [bench.to_device(maker(bs=batch, seed=s), dtype) for s in range(n_sets)]
     outs = [torch.empty(batch, 900, 256, device="cuda") for _ in sets]
     ref = None
-    for v, pf in [(v, pf) for v in variants for pf in ((0, 1, 2) if v >= 10 else (0,))]:
+    for v, pf in [(v, 0) for v in variants]:
         os.environ["DFA_FWD_VARIANT"] = str(v)
-        os.environ["DFA_FWD_PREFETCH"] = str(pf)
         fns = [(lambda g=g, o=o: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o))
                for g, o in zip(sets, outs)]
         ms = bench.time_graph(fns, 200, 20, True, torch.cuda.synchronize) / 200
