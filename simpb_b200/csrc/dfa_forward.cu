@@ -1016,7 +1016,11 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   // 10..12 = row-merging kernel (fewer DRAM bytes and L1 wavefronts, longer dependent chain per
   // warp: within 5-25 % of the default); 0 = one-warp-per-group kernel.
   // A variant whose shape constraints are not met falls through to the next family.
-  const int variant = env_int("DFA_FWD_VARIANT", 1);
+  // Default (no override): the row-sliced kernel; for bfloat16 tables, whose rows are half as long,
+  // two taps in flight per thread on small grids and the row-merging kernel on large ones measured
+  // 6-8 % faster (tools/sweep_fwd.py).
+  const bool big_grid = static_cast<long long>(d.bs) * d.A > 148 * 16;
+  const int variant = env_int("DFA_FWD_VARIANT", sizeof(T) == 2 ? (big_grid ? 11 : 2) : 1);
   if (variant >= 10) {  // merging kernel: (warps, rows in flight, CTAs per SM) per variant
     const int vpl = merge_vpl<T>(d, feat);
     if (vpl) {
