@@ -7,14 +7,20 @@ arguments, parameter names (state-dict keys) and forward signatures of
 checkpoints load and the modules can be built from the reference's config dict
 (projects/configs/simpb_nus_r50_img_704x256.py:216-239).
 
-What runs where: the four Linear layers, the two LayerNorms and the residual stay in PyTorch
-(cuBLAS / ATen); everything between them is three launches of libdfa_b200 —
-    dfa_keypoints_project   anchors (+ learnable offsets) -> sampling locations [bs,A,P,K,2]
-    dfa_softmax_weights     weights_fc logits -> softmax over cams x levels x points, attn-drop,
-                            laid out [bs,A,P,K,L,G]
-    dfa_forward             the aggregation itself
-each with its backward, instead of the ~40 small ATen kernels and the 9 MB permute copy of the
-reference's forward.  There is no grid_sample / CPU path: `use_deformable_func=False` raises.
+What runs where: the Linear layers, the two LayerNorms and the residual stay in PyTorch
+(cuBLAS / ATen); everything between them is libdfa_b200 —
+  * inference (no gradient needed): ONE launch, dfa_forward_fused — key points, camera projection,
+    softmax of the attention logits and the aggregation; neither the sampling locations nor the
+    9 MB weights tensor are materialised;
+  * training: three launches, each with its backward —
+      dfa_keypoints_project   anchors (+ learnable offsets) -> sampling locations [bs,A,P,K,2]
+      dfa_softmax_weights     weights_fc logits -> softmax over cams x levels x points, attn-drop,
+                              laid out [bs,A,P,K,L,G]
+      dfa_forward             the aggregation itself
+instead of the ~40 small ATen kernels and the 9 MB permute copy of the reference's forward.  With
+camera embedding the weights_fc GEMM runs on bs*(A+K) rows instead of bs*A*K (weights_fc is linear;
+the broadcast add happens inside the kernels).  There is no grid_sample / CPU path:
+`use_deformable_func=False` raises.
 """
 import os
 
