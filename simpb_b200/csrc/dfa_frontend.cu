@@ -114,8 +114,9 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Backward of the kernel above: one thread per (b, a) walks the anchor's P key points and K
-// cameras in a fixed order, so the gradients need no atomics and are bitwise reproducible.
+// Backward of the kernel above.  Sixteen lanes share an anchor: lane j takes key points j, j+16, ...
+// (walking the K cameras of each), the partial sums are combined by a fixed xor-shuffle tree, so the
+// gradients need no atomics and are bitwise reproducible.
 // grad_anchor [bs,A,11] (velocity entries get 0), grad_logits [bs,A,(P-F)*3] (may be NULL).
 __global__ void __launch_bounds__(128)
     dfa_keypoints_project_bwd_kernel(const float *__restrict__ anchor, const float *__restrict__ fix_scale,
@@ -123,14 +124,17 @@ __global__ void __launch_bounds__(128)
                                      const float *__restrict__ proj, const float *__restrict__ wh,
                                      const float *__restrict__ grad_loc, float *__restrict__ grad_anchor,
                                      float *__restrict__ grad_logits, int bs, int A, int P, int K) {
-  const long long ba = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (ba >= static_cast<long long>(bs) * A) return;
+  const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long ba_raw = gid >> 4;
+  const int j = static_cast<int>(gid & 15);
+  const bool active = ba_raw < static_cast<long long>(bs) * A;
+  const long long ba = active ? ba_raw : 0;  // idle half-warps compute on anchor 0 and write nothing
   const int b = static_cast<int>(ba / A);
   const float *an = anchor + ba * 11;
   const float size[3] = {expf(an[3]), expf(an[4]), expf(an[5])};
   const float sn = an[6], cs = an[7];
-  float g_ctr[3] = {0.f, 0.f, 0.f}, g_size[3] = {0.f, 0.f, 0.f}, g_sn = 0.f, g_cs = 0.f;
-  for (int p = 0; p < P; ++p) {
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // centre xyz, size xyz, sin, cos
+  for (int p = j; p < P; p += 16) {
     float off[3], dsig[3] = {0.f, 0.f, 0.f};
     if (p < num_fix) {
       off[0] = fix_scale[3 * p], off[1] = fix_scale[3 * p + 1], off[2] = fix_scale[3 * p + 2];
@@ -149,12 +153,12 @@ __global__ void __launch_bounds__(128)
     float gx = 0.f, gy = 0.f, gz = 0.f;
     for (int k = 0; k < K; ++k) {
       const float *m = proj + (static_cast<size_t>(b) * K + k) * 16;
-      const float *gl = grad_loc + ((ba * P + p) * K + k) * 2;
+      const float2 gl = __ldg(reinterpret_cast<const float2 *>(grad_loc) + (ba * P + p) * K + k);
       const float u = fmaf(m[2], z, fmaf(m[1], y, m[0] * x)) + m[3];
       const float v = fmaf(m[6], z, fmaf(m[5], y, m[4] * x)) + m[7];
       const float dpt = fmaf(m[10], z, fmaf(m[9], y, m[8] * x)) + m[11];
       const float den = fmaxf(dpt, 1e-5f);
-      float gpx = gl[0], gpy = gl[1];
+      float gpx = gl.x, gpy = gl.y;
       if (wh) gpx /= wh[(b * K + k) * 2], gpy /= wh[(b * K + k) * 2 + 1];
       const float gu = gpx / den, gv = gpy / den;
       // d/d den of (u/den, v/den); the clamp passes the gradient where dpt >= 1e-5 (torch.clamp)
@@ -163,22 +167,28 @@ __global__ void __launch_bounds__(128)
       gy += m[1] * gu + m[5] * gv + m[9] * gd;
       gz += m[2] * gu + m[6] * gv + m[10] * gd;
     }
-    g_ctr[0] += gx, g_ctr[1] += gy, g_ctr[2] += gz;
+    acc[0] += gx, acc[1] += gy, acc[2] += gz;
     const float go[3] = {cs * gx + sn * gy, -sn * gx + cs * gy, gz};  // wrt the rotated-back offset
-    g_cs += ox * gx + oy * gy;
-    g_sn += -oy * gx + ox * gy;
+    acc[7] += ox * gx + oy * gy;
+    acc[6] += -oy * gx + ox * gy;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) g_size[i] += off[i] * go[i];
-    if (p >= num_fix && grad_logits) {
+    for (int i = 0; i < 3; ++i) acc[3 + i] += off[i] * go[i];
+    if (active && p >= num_fix && grad_logits) {
       float *o = grad_logits + ba * (P - num_fix) * 3 + (p - num_fix) * 3;
 #pragma unroll
       for (int i = 0; i < 3; ++i) o[i] = go[i] * size[i] * dsig[i];
     }
   }
-  float *ga = grad_anchor + ba * 11;
-  ga[0] = g_ctr[0], ga[1] = g_ctr[1], ga[2] = g_ctr[2];
-  ga[3] = g_size[0] * size[0], ga[4] = g_size[1] * size[1], ga[5] = g_size[2] * size[2];  // d exp
-  ga[6] = g_sn, ga[7] = g_cs, ga[8] = 0.f, ga[9] = 0.f, ga[10] = 0.f;
+#pragma unroll
+  for (int mk = 8; mk > 0; mk >>= 1)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], mk);
+  if (active && j == 0) {
+    float *ga = grad_anchor + ba * 11;
+    ga[0] = acc[0], ga[1] = acc[1], ga[2] = acc[2];
+    ga[3] = acc[3] * size[0], ga[4] = acc[4] * size[1], ga[5] = acc[5] * size[2];  // d exp
+    ga[6] = acc[6], ga[7] = acc[7], ga[8] = 0.f, ga[9] = 0.f, ga[10] = 0.f;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -567,8 +577,9 @@ int dfa_keypoints_project_backward(const float *anchor, const float *fix_scale, 
     return DFA_ERR_BAD_DIMS;
   if (num_fix < num_pts && !learnable_logits) return DFA_ERR_NULL_POINTER;
   const long long n = static_cast<long long>(bs) * num_anchors;
-  if (n * num_pts >= (1ll << 31)) return DFA_ERR_BAD_DIMS;
-  dfa_keypoints_project_bwd_kernel<<<static_cast<int>((n + 127) / 128), 128, 0,
+  if (n * num_pts >= (1ll << 31) || n * 16 >= (1ll << 31)) return DFA_ERR_BAD_DIMS;
+  if (!aligned(grad_sampling_location, 8)) return DFA_ERR_MISALIGNED;  // read as (x, y) pairs
+  dfa_keypoints_project_bwd_kernel<<<static_cast<int>((n * 16 + 127) / 128), 128, 0,
                                      static_cast<cudaStream_t>(stream)>>>(
       anchor, fix_scale, num_fix, learnable_logits, projection_mat, image_wh, grad_sampling_location,
       grad_anchor, grad_learnable_logits, bs, num_anchors, num_pts, num_cams);
