@@ -17,6 +17,7 @@ from simpb_b200 import blocks, deformable_aggregation_function, feature_maps_for
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--train", action="store_true", help="time forward + backward of ONE layer in training mode")
 a = ap.parse_args()
 torch.manual_seed(0)
 cfg = dict(embed_dims=256, num_groups=8, num_levels=4, num_cams=6, attn_drop=0.15,
@@ -60,6 +61,47 @@ def run_ref(g):
                                                 w.permute(0, 1, 4, 2, 3, 5).contiguous())
         x = r.output_proj(feats)
     return x
+
+
+def train_step(front, g):
+    """forward + backward of one DFA layer with gradients for inputs, feature table and parameters."""
+    inst = g["instance_feature"].detach().requires_grad_()
+    col = g["fm"][0].detach().requires_grad_()
+    if front == "fused":
+        m = layers[0]
+        out = m(inst, g["anchor"], g["anchor_embed"], [col, g["fm"][1], g["fm"][2]], g["metas"])
+    else:
+        r = refs[0]
+        logits = r.kps_generator.learnable_fc(inst)
+        pts = module_ref.key_points(g["anchor"], r.kps_generator.fix_scale, logits)
+        keep = (torch.rand(a.batch, 900, 6, 1, 13, 1, device="cuda") > 0.15)
+        w = r.attention_weights(inst, g["anchor_embed"], g["projection_mat"], drop_mask=keep)
+        uv = module_ref.project_points(pts, g["projection_mat"], g["image_wh"])
+        feats = deformable_aggregation_function(col, g["fm"][1], g["fm"][2], uv.permute(0, 2, 3, 1, 4).contiguous(),
+                                                w.permute(0, 1, 4, 2, 3, 5).contiguous())
+        out = torch.cat([r.output_proj(feats), inst], -1)
+    out.sum().backward()
+
+
+if a.train:
+    for m in layers + refs:
+        m.train()
+    res = {"config": "1 x DFA layer forward + backward, training mode (attn-drop 0.15), bs=%d, 900 anchors" % a.batch}
+    for front in ("fused", "torch_front_end"):
+        for _ in range(3):
+            for g in frames:
+                train_step(front, g)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            for g in frames:
+                train_step(front, g)
+        e1.record()
+        torch.cuda.synchronize()
+        res[front + "_eager_ms_per_step"] = round(e0.elapsed_time(e1) / (10 * len(frames)), 4)
+    print(json.dumps(res))
+    sys.exit(0)
 
 
 def timeit(fn, graph):
