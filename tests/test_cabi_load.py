@@ -46,6 +46,41 @@ def test_argument_validation_needs_no_gpu():
     assert cabi.lib.dfa_forward_host_workspace_bytes(0, ctypes.byref(d)) > 4 * 100 * 256
 
 
+def test_argument_validation_of_the_other_entry_points():
+    """Every entry point refuses null pointers and nonsense sizes with a DFA_ERR_* code before
+    touching the device."""
+    from simpb_b200 import cabi
+    lib = cabi.lib
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    d = cabi.Dims(1, 6, 100, 256, 4, 9, 13, 8)
+    assert lib.dfa_backward(p, 0, p, p, p, p, None, p, p, p, ctypes.byref(d), 0, None) == -1
+    assert lib.dfa_backward(p, 0, p, p, p, p, p, None, p, p, ctypes.byref(cabi.Dims(1, 6, 100, 250, 4, 9, 13, 8)),
+                            0, None) == -2                       # NULL grad_feat is allowed; dims are not
+    assert lib.dfa_forward_fused(p, 0, p, p, None, p, 7, p, p, p, p, p, p, None, ctypes.byref(d), None) == -1
+    assert lib.dfa_forward_fused(p, 0, p, p, p, p, 20, p, p, p, p, p, p, None, ctypes.byref(d), None) == -2
+    odd_groups = cabi.Dims(1, 6, 100, 255, 4, 9, 13, 5)          # G not a power of two: caller falls back
+    assert lib.dfa_forward_fused(p, 0, p, p, p, p, 7, p, p, p, p, p, p, None, ctypes.byref(odd_groups), None) == -5
+    assert lib.dfa_debug_indices(p, p, None, p, p, ctypes.byref(d), None) == -1
+    assert lib.dfa_flatten_maps(None, p, 4, 1, 6, 256, p, 0, None) == -1
+    assert lib.dfa_flatten_maps(p, p, 0, 1, 6, 256, p, 0, None) == -2
+    assert lib.dfa_keypoints_project(p, p, 7, None, p, p, None, p, 1, 9, 13, 6, None) == -1   # learnable pts need logits
+    assert lib.dfa_keypoints_project(p, p, 14, p, p, p, None, p, 1, 9, 13, 6, None) == -2     # more fixed than total
+    assert lib.dfa_keypoints_project_backward(p, p, 7, p, p, p, None, p, p, 1, 9, 13, 6, None) == -1
+    assert lib.dfa_softmax_weights(None, None, 1.0, p, 1, 9, 6, 4, 13, 8, None) == -1
+    assert lib.dfa_softmax_weights(p, None, 1.0, p, 1, 9, 6, 4, 13, 7, None) == -5            # 256 % G != 0
+    assert lib.dfa_softmax_weights_split(p, None, None, 1.0, p, 1, 9, 6, 4, 13, 8, None) == -1
+    assert lib.dfa_softmax_weights_backward(p, None, 1.0, p, None, 1, 9, 6, 4, 13, 8, None) == -1
+    assert lib.dfa_softmax_weights_split_backward(p, p, None, 1.0, p, p, None, 1, 9, 6, 4, 13, 8, None) == -1
+    assert lib.dfa_msda_forward(p, 0, p, p, p, None, p, 1, 100, 8, 32, 9, 4, 4, 1, None, None) == -1
+    assert lib.dfa_msda_forward(p, 0, p, p, p, p, p, 1, 100, 8, 0, 9, 4, 4, 1, None, None) == -2
+    assert lib.dfa_msda_forward(p, 0, p, p, p, p, p, 1, 100, 8, 32, 9, 4, 4, 3, None, None) == -1   # groups need a table
+    assert lib.dfa_msda_forward(p, 9, p, p, p, p, p, 1, 100, 8, 32, 9, 4, 4, 1, None, None) == -3
+    assert lib.dfa_msda_backward(p, 0, p, p, p, p, p, None, None, p, 1, 100, 8, 32, 9, 4, 4, 1, None, 1, None) == -1
+    for code in (-1, -2, -3, -4, -5):
+        assert lib.dfa_error_string(code).startswith(b"dfa:")
+
+
 def test_cpu_tensors_are_rejected_loudly():
     from simpb_b200 import cabi, deformable_aggregation_function
     t = torch.zeros(1, 4, 8)
