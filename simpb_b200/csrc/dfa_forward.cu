@@ -8,6 +8,9 @@
 // row-sliced (default), row-merging, one warp per group; plus a shape-generic fallback.
 // The weighted sum lives in registers and the output row is written once: no atomics and no
 // zero-filled output (the reference: one float atomic per thread on an at::zeros tensor).
+#include <atomic>
+#include <mutex>
+
 #include "dfa_common.cuh"
 
 namespace {
@@ -941,6 +944,12 @@ __global__ void dfa_debug_indices_kernel(const int *__restrict__ shape, const in
   }
 }
 
+}  // namespace
+
+#include "dfa_forward_pool.cuh"
+
+namespace {
+
 // ------------------------------------------------------------------------------------------
 // launchers and dispatch
 // ------------------------------------------------------------------------------------------
@@ -1021,7 +1030,7 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   // 6-8 % faster (tools/sweep_fwd.py).
   const bool big_grid = static_cast<long long>(d.bs) * d.A > 148 * 16;
   const int variant = env_int("DFA_FWD_VARIANT", sizeof(T) == 2 ? (big_grid ? 11 : 2) : 1);
-  if (variant >= 10) {  // merging kernel: (warps, rows in flight, CTAs per SM) per variant
+  if (variant >= 10 && variant < 20) {  // merging kernel: (warps, rows in flight, CTAs per SM) per variant
     const int vpl = merge_vpl<T>(d, feat);
     if (vpl) {
       const bool tma = warp_tma_ok(d, loc, w);
@@ -1036,6 +1045,21 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
       }
 #undef WARPV
 #undef WARPK
+    }
+  }
+  if (variant >= 20) {  // SM-pooled kernel: 20 = one 1024-thread CTA per SM, 21 = two 512-thread CTAs
+    const int vpl = pool_vpl<T>(d, feat, loc, out);
+    if (vpl) {
+      int rc;
+#define POOL(NT) (vpl == 2 ? launch_fwd_pool<T, 2, 1, NT>(feat, shape, start, loc, w, out, d, st)   \
+                           : launch_fwd_pool<T, 1, 2, NT>(feat, shape, start, loc, w, out, d, st))
+      if (variant == 21) rc = POOL(512);
+      else if (variant == 22)   // 768 threads: 85 registers, twice the taps in flight per lane
+        rc = vpl == 2 ? launch_fwd_pool<T, 2, 2, 768>(feat, shape, start, loc, w, out, d, st)
+                      : launch_fwd_pool<T, 1, 4, 768>(feat, shape, start, loc, w, out, d, st);
+      else rc = POOL(1024);
+#undef POOL
+      if (rc >= 0) return rc;
     }
   }
   const int rvariant = variant >= 10 ? 1 : variant;

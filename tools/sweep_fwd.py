@@ -10,6 +10,8 @@ import bench  # noqa: E402
 
 variants = [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,2,10,11,12").split(",")]
 cases = [("rig", 1, "f32"), ("uniform", 1, "f32"), ("rig", 8, "f32"), ("rig", 1, "bf16"), ("rig", 8, "bf16")]
+if len(sys.argv) > 2:      # e.g. "rig:1:f32,rig:8:f32"
+    cases = [(c.split(":")[0], int(c.split(":")[1]), c.split(":")[2]) for c in sys.argv[2].split(",")]
 for inputs, batch, dt in cases:
     maker = synthetic.rig_op_inputs if inputs == "rig" else synthetic.op_inputs_uniform
     dtype = torch.float32 if dt == "f32" else torch.bfloat16
