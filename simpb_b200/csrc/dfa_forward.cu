@@ -24,8 +24,17 @@ __device__ long long *g_phase_buf = nullptr;
     if (g_phase_buf && lane == 0)                                                         \
       g_phase_buf[(static_cast<size_t>(blockIdx.x) * NW + warp) * 8 + (i)] = clock64();   \
   } while (0)
+#define DFA_GSTAMP(i)                                                                      \
+  do {                                                                                     \
+    if (g_phase_buf && lane == 0) {                                                        \
+      unsigned long long gt_;                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                              \
+      g_phase_buf[(static_cast<size_t>(blockIdx.x) * NW + warp) * 8 + (i)] = static_cast<long long>(gt_); \
+    }                                                                                      \
+  } while (0)
 #else
 #define DFA_STAMP(i) do {} while (0)
+#define DFA_GSTAMP(i) do {} while (0)
 #endif
 
 // ------------------------------------------------------------------------------------------
@@ -188,6 +197,7 @@ __global__ void __launch_bounds__(NT, MINB)
   const int lane = tid & 31, warp = tid >> 5;
 #endif
   DFA_STAMP(0);
+  DFA_GSTAMP(6);
   const int anchor = blockIdx.x;  // b * A + a
   const int b = anchor / d.A;
   const int PK = d.P * d.K, wcount = PK * d.L * d.G;
@@ -288,186 +298,10 @@ __global__ void __launch_bounds__(NT, MINB)
     out[static_cast<size_t>(anchor) * d.C + c] = sum;
   }
   DFA_STAMP(5);
+  DFA_GSTAMP(7);
 }
 
 
-
-// ------------------------------------------------------------------------------------------
-// forward, row-sliced mapping with coefficient records ("lean" variant)
-// ------------------------------------------------------------------------------------------
-// Same thread mapping as dfa_fwd_rows_kernel, different operand handling.  The anchor's 10 KB
-// weights block is NOT staged: once the valid samples are known, the CTA reads just their weight
-// lines from global memory (camera-rig inputs: 81 % of the weight bytes never leave HBM) and folds
-// them into the tap records, cw[tap][group][corner] = bilinear(corner) * weight[group] — the same
-// product the other kernel forms in its loop, so the results are bit-identical.  Per tap a thread then
-// reads two shared-memory vectors (corner offsets, its group's four coefficients) instead of four
-// words and does no multiplies outside the FFMA2s; the CTA's shared memory drops from 26.7 KB to
-// ~20 KB, which the SM gives back to L1.  Records cover TCAP taps at a time; anchors with more valid
-// taps loop over chunks (accumulators stay in registers).
-struct SmemLayout3 {
-  uint32_t loc, off, cw, list, tab, red, bar, total;
-};
-__host__ __device__ inline SmemLayout3 smem_layout3(int P, int K, int L, int G, int C, int slices, int tcap) {
-  SmemLayout3 s;
-  uint32_t o = 0;
-  s.cw = o, o = align_up(o + 16u * G * tcap, 128);
-  s.off = o, o = align_up(o + 16u * tcap, 16);
-  s.loc = o, o = align_up(o + 8u * P * K, 16);
-  s.list = o, o = align_up(o + 4u * P * K, 16);
-  s.tab = o, o = align_up(o + 12u * K * L, 16);
-  s.red = o, o = align_up(o + 4u * slices * C, 16);
-  s.bar = o, o += 32;
-  s.total = o;
-  return s;
-}
-
-template <typename T, bool TMA, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-    dfa_fwd_rows2_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
-                         const int *__restrict__ start, const float *__restrict__ loc,
-                         const float *__restrict__ weights, float *__restrict__ out, Dims d,
-                         int vpr_log2, int tcap) {
-  constexpr int VEC = FeatVec<T>::VEC;
-  constexpr int MAXI = 3;  // weight loads in flight per thread while the records are built
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int vpr = 1 << vpr_log2;
-  const int slices = NT >> vpr_log2;
-  const SmemLayout3 lay = smem_layout3(d.P, d.K, d.L, d.G, d.C, slices, tcap);
-  float4 *s_cw = reinterpret_cast<float4 *>(smem + lay.cw);
-  uint4 *s_off = reinterpret_cast<uint4 *>(smem + lay.off);
-  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
-  int *s_list = reinterpret_cast<int *>(smem + lay.list);
-  int *s_tab = reinterpret_cast<int *>(smem + lay.tab);
-  float *s_red = reinterpret_cast<float *>(smem + lay.red);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
-  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
-
-  const int tid = threadIdx.x;
-  const int anchor = blockIdx.x;  // b * A + a
-  const int b = anchor / d.A;
-  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
-  const float *loc_g = loc + static_cast<size_t>(anchor) * PK * 2;
-  const float *w_g = weights + static_cast<size_t>(anchor) * wcount;
-
-  if (TMA) {
-    if (tid == 0) {
-      mbar_init(&bars[0], 1);
-      fence_mbar_init();
-      mbar_expect_tx(&bars[0], 8u * PK);
-      tma_bulk_g2s(s_loc, loc_g, 8u * PK, &bars[0]);
-    }
-  } else {
-    for (int i = tid; i < 2 * PK; i += NT) s_loc[i] = __ldg(loc_g + i);
-  }
-  for (int i = tid; i < d.K * d.L; i += NT) {
-    s_tab[3 * i] = __ldg(shape + 2 * i);
-    s_tab[3 * i + 1] = __ldg(shape + 2 * i + 1);
-    s_tab[3 * i + 2] = __ldg(start + i);
-  }
-  __syncthreads();
-  if (tid < 32) {
-    if (TMA) mbar_wait(&bars[0], 0);
-    int n = 0;
-    for (int base = 0; base < PK; base += 32) {
-      const int s = base + tid;
-      bool v = false;
-      if (s < PK) v = sample_valid(s_loc[2 * s], s_loc[2 * s + 1]);
-      const unsigned m = __ballot_sync(0xffffffffu, v);
-      if (v) s_list[n + __popc(m & ((1u << tid) - 1u))] = s;
-      n += __popc(m);
-    }
-    if (tid == 0) *s_nvalid = n;
-  }
-  __syncthreads();
-  const int nv = *s_nvalid;
-  const int ntaps = nv * d.L;
-
-  const int slice = tid >> vpr_log2, v = tid & (vpr - 1);
-  const int ch = v * VEC;
-  const int grp = ch / (d.C / d.G);
-  const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
-                            static_cast<size_t>(b) * d.num_feat * d.C * sizeof(T) +
-                            static_cast<uint32_t>(ch) * sizeof(T);
-  const uint32_t rb = static_cast<uint32_t>(d.C) * sizeof(T);
-  float acc[VEC];
-#pragma unroll
-  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-
-  for (int c0 = 0; c0 < ntaps; c0 += tcap) {
-    const int nrec = ntaps - c0 < tcap ? ntaps - c0 : tcap;
-    const int nrec_pad = (nrec + slices - 1) / slices * slices;  // tcap is a multiple of slices
-    // records: item = (tap, group); the weight loads of up to MAXI items go out first
-    const int nitems = nrec_pad * d.G;
-    for (int i0 = tid; i0 < nitems; i0 += NT * MAXI) {
-      float wv[MAXI];
-      int smp[MAXI], lv[MAXI];
-#pragma unroll
-      for (int j = 0; j < MAXI; ++j) {
-        const int it = i0 + j * NT;
-        const int r = it / d.G, g = it - r * d.G;
-        wv[j] = 0.f, smp[j] = -1, lv[j] = 0;
-        if (it < nitems && r < nrec) {
-          const int t = c0 + r;
-          const int l = t / nv, i = t - l * nv;  // level-major: coarse-level neighbours back to back
-          smp[j] = s_list[i], lv[j] = l;
-          wv[j] = __ldg(w_g + (smp[j] * d.L + l) * d.G + g);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < MAXI; ++j) {
-        const int it = i0 + j * NT;
-        if (it >= nitems) break;
-        const int r = it / d.G, g = it - r * d.G;
-        float4 cw = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint4 off = make_uint4(0u, 0u, 0u, 0u);
-        if (smp[j] >= 0) {
-          const int s = smp[j];
-          const int kl = (s % d.K) * d.L + lv[j];
-          TapGeom gm;
-          tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], s_tab[3 * kl], s_tab[3 * kl + 1], s_tab[3 * kl + 2], gm);
-          // a corner outside the map is redirected to an in-map corner of the tap with a zero
-          // coefficient (a valid sample always has one): the gather needs no predicates
-          const int safe = gm.row[0] >= 0 ? gm.row[0] : gm.row[1] >= 0 ? gm.row[1]
-                         : gm.row[2] >= 0 ? gm.row[2] : gm.row[3];
-          off.x = (gm.row[0] >= 0 ? gm.row[0] : safe) * rb, cw.x = gm.row[0] >= 0 ? (gm.hh * gm.hw) * wv[j] : 0.f;
-          off.y = (gm.row[1] >= 0 ? gm.row[1] : safe) * rb, cw.y = gm.row[1] >= 0 ? (gm.hh * gm.lw) * wv[j] : 0.f;
-          off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, cw.z = gm.row[2] >= 0 ? (gm.lh * gm.hw) * wv[j] : 0.f;
-          off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, cw.w = gm.row[3] >= 0 ? (gm.lh * gm.lw) * wv[j] : 0.f;
-        }
-        s_cw[it] = cw;
-        if (g == 0) s_off[r] = off;  // padding taps: row 0 of the batch item, zero coefficients
-      }
-    }
-    __syncthreads();
-    if (slice < slices) {
-      for (int r = slice; r < nrec_pad; r += slices) {
-        const uint4 off = s_off[r];
-        const typename FeatVec<T>::raw_t v0 = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + off.x));
-        const typename FeatVec<T>::raw_t v1 = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + off.y));
-        const typename FeatVec<T>::raw_t v2 = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + off.z));
-        const typename FeatVec<T>::raw_t v3 = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + off.w));
-        const float4 cw = s_cw[r * d.G + grp];
-        FeatVec<T>::fma(acc, cw.x, v0);
-        FeatVec<T>::fma(acc, cw.y, v1);
-        FeatVec<T>::fma(acc, cw.z, v2);
-        FeatVec<T>::fma(acc, cw.w, v3);
-      }
-    }
-    if (c0 + tcap < ntaps) __syncthreads();  // the next chunk rewrites the records
-  }
-  if (slice < slices) {
-    float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
-#pragma unroll
-    for (int c = 0; c < VEC / 4; ++c)
-      r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-  }
-  __syncthreads();
-  for (int c = tid; c < d.C; c += NT) {
-    float sum = 0.f;
-    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
-    out[static_cast<size_t>(anchor) * d.C + c] = sum;
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // fused module forward: key points + projection + softmax of the attention logits + gather
@@ -1166,22 +1000,6 @@ int launch_fwd_rows(const void *feat, const int *shape, const int *start, const 
   return static_cast<int>(cudaGetLastError());
 }
 
-template <typename T, bool TMA, int NT, int MINB>
-int launch_fwd_rows2(const void *feat, const int *shape, const int *start, const float *loc,
-                     const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
-  auto kern = dfa_fwd_rows2_kernel<T, TMA, NT, MINB>;
-  const int slices = NT / vpr;
-  int vpr_log2 = 0;
-  while ((1 << vpr_log2) < vpr) ++vpr_log2;
-  int tcap = env_int("DFA_FWD_TCAP", 96);
-  tcap = (tcap < slices ? slices : tcap) / slices * slices;
-  const SmemLayout3 lay = smem_layout3(d.P, d.K, d.L, d.G, d.C, slices, tcap);
-  if (int rc = set_smem(kern, lay.total)) return rc;
-  kern<<<d.bs * d.A, NT, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w, out, d,
-                                          vpr_log2, tcap);
-  return static_cast<int>(cudaGetLastError());
-}
-
 // Row-sliced fast path: the row is a power-of-two number of 16-byte vectors (<= block size) and
 // every vector lies inside one channel group.
 template <typename T>
@@ -1257,20 +1075,13 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   }
   const int rvariant = variant >= 10 ? 1 : variant;
   if (rvariant >= 1) {
-    const int nt = (rvariant == 3 || rvariant == 4) ? 512 : 256;
+    const int nt = rvariant >= 3 ? 512 : 256;
     const int vpr = rows_vpr<T>(d, feat, nt);
     if (vpr) {
       const bool tma = tma_ok(d, loc, w);
 #define ROWS(U, NT, MINB)                                                                        \
   (tma ? launch_fwd_rows<T, U, true, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st)        \
        : launch_fwd_rows<T, U, false, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st))
-      const bool loc_tma = (8ll * d.P * d.K) % 16 == 0 && aligned(loc, 16);
-      if (rvariant == 5)   // lean records, 6 CTAs per SM
-        return loc_tma ? launch_fwd_rows2<T, true, 256, 6>(feat, shape, start, loc, w, out, d, vpr, st)
-                       : launch_fwd_rows2<T, false, 256, 6>(feat, shape, start, loc, w, out, d, vpr, st);
-      if (rvariant == 6)   // lean records, 7 CTAs per SM when the registers allow
-        return loc_tma ? launch_fwd_rows2<T, true, 256, 7>(feat, shape, start, loc, w, out, d, vpr, st)
-                       : launch_fwd_rows2<T, false, 256, 7>(feat, shape, start, loc, w, out, d, vpr, st);
       switch (rvariant) {
         case 1: return ROWS(1, 256, 6);
         case 2: return ROWS(2, 256, 4);

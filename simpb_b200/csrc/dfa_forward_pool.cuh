@@ -94,7 +94,6 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1)
                         const float *__restrict__ weights, float *__restrict__ out, Dims d,
                         PoolArgs pa) {
   constexpr int VEC = FeatVec<T>::VEC;
-  constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const int NB = pa.NB;
   const PoolLayout lay = pool_layout(d.P, d.K, d.L, d.C, NB, pa.capt);

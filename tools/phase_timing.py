@@ -73,5 +73,29 @@ for i in range(1, 8):
 last = 5 if a.variant < 10 else 7
 life = (t[:, :, last].max(dim=1).values - t0[:, 0])
 print("CTA lifetime: median %.0f p90 %.0f max %.0f cycles" % (life.median(), life.quantile(0.9), life.max()))
+if a.variant < 10:     # globaltimer (ns) at CTA start / end: launch ramp and tail in wall time
+    gs, ge = t[:, 0, 6], t[:, :, 7].max(dim=1).values
+    first = gs.min()
+    print("wall clock (globaltimer, us): CTA starts  median %.2f  p90 %.2f  max %.2f   |   CTA ends  median %.2f  p90 %.2f  "
+          "p99 %.2f  max %.2f" % tuple(float(x) / 1e3 for x in (
+              (gs - first).median(), (gs - first).quantile(0.9), (gs - first).max(), (ge - first).median(),
+              (ge - first).quantile(0.9), (ge - first).quantile(0.99), (ge - first).max())))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g = sets[0]
+    lib.dfa_debug_set_phase_buffer(None)
+    torch.cuda.synchronize()
+    e0.record()
+    lib.dfa_forward(g["feat"].data_ptr(), 0, g["shape"].data_ptr(), g["start"].data_ptr(), g["loc"].data_ptr(),
+                    g["w"].data_ptr(), out.data_ptr(), ctypes.byref(dm), st)
+    e1.record()
+    torch.cuda.synchronize()
+    print("event time of one isolated launch (no stamps written): %.2f us" % (e0.elapsed_time(e1) * 1e3))
+    nvalid = ((sets[2]["loc"] > 0) & (sets[2]["loc"] < 1)).all(-1).flatten(2).sum(-1).flatten().cpu().double()
+    lf = (ge - gs) / 1e3
+    order = torch.argsort(lf, descending=True)[:8]
+    print("longest-lived anchors: " + ", ".join("%d valid samples %.1f us (start +%.1f)" % (
+        int(nvalid[i]), float(lf[i]), float(gs[i] - first) / 1e3) for i in order))
+    print("valid samples per anchor: median %d  p90 %d  max %d;  corr(life, valid) = %.2f"
+          % (nvalid.median(), nvalid.quantile(0.9), nvalid.max(), float(torch.corrcoef(torch.stack([lf, nvalid]))[0, 1])))
 span = t[:, :, last].max() - t[:, :, 0][t[:, :, 0] > 0].min()
 print("(clock64 is per SM; first start to last end across SMs is only indicative: %.0f cycles)" % span)
