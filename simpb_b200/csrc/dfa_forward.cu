@@ -174,12 +174,25 @@ __global__ void __launch_bounds__(NT, MINB)
     dfa_fwd_rows_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
                         const int *__restrict__ start, const float *__restrict__ loc,
                         const float *__restrict__ weights, float *__restrict__ out, Dims d,
-                        int vpr_log2) {
+                        int vpr_log2, int split_from, int split_log2) {
   constexpr int VEC = FeatVec<T>::VEC;
   extern __shared__ __align__(128) unsigned char smem[];
+  // Channel split (small grids): CTAs from `split_from` on share an anchor 2^split_log2 ways, each
+  // taking a contiguous block of channels — a quarter row per load and four times the slices, so the
+  // anchor's chain of dependent load rounds is a quarter as long; every CTA writes its own channels,
+  // nothing is combined.  The launcher splits the anchors that do not fit the first wave.
+  int anchor = blockIdx.x;  // b * A + a
+  int ch_base = 0, Cs = d.C;
+  if (static_cast<int>(blockIdx.x) >= split_from) {
+    const int r = blockIdx.x - split_from;
+    anchor = split_from + (r >> split_log2);
+    Cs = d.C >> split_log2;
+    ch_base = (r & ((1 << split_log2) - 1)) * Cs;
+    vpr_log2 -= split_log2;
+  }
   const int vpr = 1 << vpr_log2;
   const int slices = NT >> vpr_log2;
-  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
+  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, Cs, slices, slices * U);
   float *s_w = reinterpret_cast<float *>(smem + lay.w);
   float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
   uint4 *s_off = reinterpret_cast<uint4 *>(smem + lay.off);
@@ -198,7 +211,6 @@ __global__ void __launch_bounds__(NT, MINB)
 #endif
   DFA_STAMP(0);
   DFA_GSTAMP(6);
-  const int anchor = blockIdx.x;  // b * A + a
   const int b = anchor / d.A;
   const int PK = d.P * d.K, wcount = PK * d.L * d.G;
 
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(NT, MINB)
   DFA_STAMP(3);
 
   const int slice = tid >> vpr_log2, v = tid & (vpr - 1);
-  const int ch = v * VEC;
+  const int ch = ch_base + v * VEC;
   float acc[VEC];
 #pragma unroll
   for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
@@ -285,17 +297,17 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
         for (int q = 0; q < 4; ++q) FeatVec<T>::fma(acc, cw[u][q], val[u][q]);
     }
-    float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
+    float4 *r = reinterpret_cast<float4 *>(s_red + slice * Cs + (ch - ch_base));
 #pragma unroll
     for (int c = 0; c < VEC / 4; ++c)
       r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
   }
   DFA_STAMP(4);
   __syncthreads();
-  for (int c = tid; c < d.C; c += NT) {
+  for (int c = tid; c < Cs; c += NT) {
     float sum = 0.f;
-    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
-    out[static_cast<size_t>(anchor) * d.C + c] = sum;
+    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * Cs + c];
+    out[static_cast<size_t>(anchor) * d.C + ch_base + c] = sum;
   }
   DFA_STAMP(5);
   DFA_GSTAMP(7);
@@ -989,14 +1001,44 @@ int launch_fwd_t(const void *feat, const int *shape, const int *start, const flo
 template <typename T, int U, bool TMA, int NT, int MINB>
 int launch_fwd_rows(const void *feat, const int *shape, const int *start, const float *loc,
                     const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
+  constexpr int VEC = FeatVec<T>::VEC;
   auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB>;
   const int slices = NT / vpr;
   int vpr_log2 = 0;
   while ((1 << vpr_log2) < vpr) ++vpr_log2;
-  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
+  // Channel split.  The anchors of the last, partial wave of resident CTAs start only when earlier
+  // anchors retire and then end the kernel (R50, bs=1: 900 anchors on 888 slots; the 12 late CTAs
+  // were the last to finish): they are split four ways by channels, which makes their CTAs a quarter
+  // as long.  Measured: 19.2 -> 17.9 us at bs=1 / 900 anchors, 24.8 -> 23.5 us at 1220 anchors,
+  // 31.6 -> 30.3 us at bs=2, neutral from bs=4 on.  DFA_FWD_SPLIT: 0 = never, 1 = as described
+  // (default), 2 / 3 = every anchor two / four ways (experiments: par / slower).
+  const long long total = static_cast<long long>(d.bs) * d.A;
+  long long split_from = total, grid = total;
+  int split_log2 = 0;
+  const int mode = env_int("DFA_FWD_SPLIT", 1);
+  const int max_log2 = ((d.C / 4) % VEC == 0 && vpr >= 4) ? 2 : (((d.C / 2) % VEC == 0 && vpr >= 2) ? 1 : 0);
+  if (mode == 1 && max_log2 == 2) {
+    static int sm_count[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+      if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+      const long long slots = static_cast<long long>(sm_count[dev]) * MINB;
+      const long long rem = slots > 0 ? total % slots : 0;  // anchors of the last, partial wave
+      const int frac = env_int("DFA_FWD_SPLIT_FRAC", 2);  // split when the last wave is at most 1/frac full
+      if (total > slots && rem > 0 && frac > 0 && rem <= slots / frac)
+        split_from = total - rem, split_log2 = 2, grid = split_from + 4 * rem;
+    }
+  } else if (mode >= 2 && max_log2 >= mode - 1) {
+    split_from = 0, split_log2 = mode - 1, grid = total << split_log2;
+  }
+  const int max_slices = slices << split_log2;
+  SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
+  const SmemLayout2 lay_s = smem_layout2(d.P, d.K, d.L, d.G, d.C >> split_log2, max_slices, max_slices * U);
+  if (lay_s.total > lay.total) lay = lay_s;
   if (int rc = set_smem(kern, lay.total)) return rc;
-  kern<<<d.bs * d.A, NT, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w, out, d,
-                                          vpr_log2);
+  kern<<<static_cast<unsigned int>(grid), NT, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
+                                                               out, d, vpr_log2, static_cast<int>(split_from),
+                                                               split_log2);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -158,6 +158,29 @@ def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
             assert_close(out, ref, RTOL_F32, "variant %d %s" % (variant, dtype))
 
 
+@pytest.mark.parametrize("anchors", [900, 950, 889])
+def test_forward_channel_split(anchors, monkeypatch):
+    """Row-sliced forward with channel-split CTAs: by default the anchors beyond the first wave of
+    resident CTAs (888 on a 148-SM part) are shared four ways by channel blocks; DFA_FWD_SPLIT=2/3
+    split every anchor.  Every mode agrees with the oracle; modes differ from each other only in
+    summation order."""
+    from simpb_b200 import cabi, synthetic
+    for d, dtype in ((synthetic.rig_op_inputs(bs=1, A=anchors, seed=51), torch.float32),
+                     (synthetic.op_inputs_uniform(bs=1, A=anchors, seed=52), torch.bfloat16)):
+        g = dev(d, dtype)
+        ref = oracle.forward(g["feat"].float().cpu(), d["spatial_shape"], d["scale_start_index"],
+                             d["sampling_location"], d["weights"])
+        outs = {}
+        for mode in ("0", "1", "2", "3"):
+            monkeypatch.setenv("DFA_FWD_SPLIT", mode)
+            junk = torch.full((1, anchors, g["feat"].shape[2]), float("nan"), device="cuda")
+            outs[mode] = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=junk)
+            assert_close(outs[mode], ref, RTOL_F32, "split mode %s %s" % (mode, dtype))
+            assert torch.equal(outs[mode], cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"]))
+        # anchors of the first wave are untouched by the default mode
+        assert torch.equal(outs["1"][:, :888], outs["0"][:, :888])      # 148 SMs x 6 CTAs
+
+
 @pytest.mark.parametrize("variant", [20, 21, 22])
 def test_pooled_forward_schedules(variant, monkeypatch):
     """SM-pooled forward (DFA_FWD_VARIANT 20..22): every batch schedule — even split, static
