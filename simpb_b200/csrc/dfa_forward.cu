@@ -357,12 +357,23 @@ template <typename T, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
     dfa_fwd_fused_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
                          const int *__restrict__ start, FusedArgs fa, float *__restrict__ out, Dims d,
-                         int vpr_log2) {
+                         int vpr_log2, int split_from, int split_log2) {
   constexpr int VEC = FeatVec<T>::VEC;
   extern __shared__ __align__(128) unsigned char smem[];
+  // channel split of the last wave's anchors, as in dfa_fwd_rows_kernel: every split CTA runs the
+  // whole prologue and gathers its own block of channels with 2^split_log2 times the slices
+  int anchor = blockIdx.x;  // b * A + a
+  int ch_base = 0, Cs = d.C;
+  if (static_cast<int>(blockIdx.x) >= split_from) {
+    const int r = blockIdx.x - split_from;
+    anchor = split_from + (r >> split_log2);
+    Cs = d.C >> split_log2;
+    ch_base = (r & ((1 << split_log2) - 1)) * Cs;
+    vpr_log2 -= split_log2;
+  }
   const int vpr = 1 << vpr_log2;
   const int slices = NT >> vpr_log2;
-  const SmemLayoutF layf = smem_layout_fused(d.P, d.K, d.L, d.G, d.C, slices, NT);
+  const SmemLayoutF layf = smem_layout_fused(d.P, d.K, d.L, d.G, Cs, slices, NT);
   const SmemLayout2 &lay = layf.r;
   float *s_w = reinterpret_cast<float *>(smem + lay.w);
   float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
@@ -380,7 +391,6 @@ __global__ void __launch_bounds__(NT, MINB)
   float *s_inv = reinterpret_cast<float *>(smem + layf.inv);
 
   const int tid = threadIdx.x;
-  const int anchor = blockIdx.x;  // b * A + a
   const int b = anchor / d.A;
   const int PK = d.P * d.K, LP = d.L * d.P, lpg = LP * d.G, n_el = d.K * lpg;
 #ifdef DFA_PHASE_TIMING
@@ -423,7 +433,7 @@ __global__ void __launch_bounds__(NT, MINB)
                   fa.wh ? fa.wh + (b * d.K + k) * 2 : nullptr, s_kp[3 * p], s_kp[3 * p + 1], s_kp[3 * p + 2],
                   px, py);
     s_loc[2 * s] = px, s_loc[2 * s + 1] = py;
-    if (fa.loc_out) {
+    if (fa.loc_out && ch_base == 0) {
       fa.loc_out[(static_cast<size_t>(anchor) * PK + s) * 2] = px;
       fa.loc_out[(static_cast<size_t>(anchor) * PK + s) * 2 + 1] = py;
     }
@@ -509,7 +519,7 @@ __global__ void __launch_bounds__(NT, MINB)
   DFA_STAMP(5);
 
   const int slice = tid >> vpr_log2, v = tid & (vpr - 1);
-  const int ch = v * VEC;
+  const int ch = ch_base + v * VEC;
   float acc[VEC];
 #pragma unroll
   for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
@@ -532,7 +542,7 @@ __global__ void __launch_bounds__(NT, MINB)
       FeatVec<T>::fma(acc, bw.z * wgt, val[2]);
       FeatVec<T>::fma(acc, bw.w * wgt, val[3]);
     }
-    float4 *r = reinterpret_cast<float4 *>(s_red + slice * d.C + ch);
+    float4 *r = reinterpret_cast<float4 *>(s_red + slice * Cs + (ch - ch_base));
 #pragma unroll
     for (int c = 0; c < VEC / 4; ++c)
       r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
@@ -540,10 +550,10 @@ __global__ void __launch_bounds__(NT, MINB)
   DFA_STAMP(6);
   __syncthreads();
   const int cpg = d.C / d.G;
-  for (int c = tid; c < d.C; c += NT) {
+  for (int c = tid; c < Cs; c += NT) {
     float sum = 0.f;
-    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * d.C + c];
-    out[static_cast<size_t>(anchor) * d.C + c] = sum * s_inv[c / cpg];  // the softmax denominator, once
+    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * Cs + c];
+    out[static_cast<size_t>(anchor) * d.C + ch_base + c] = sum * s_inv[(ch_base + c) / cpg];  // the softmax denominator, once
   }
   DFA_STAMP(7);
 }
@@ -998,23 +1008,18 @@ int launch_fwd_t(const void *feat, const int *shape, const int *start, const flo
     default: return CALL(1);                      \
   }
 
-template <typename T, int U, bool TMA, int NT, int MINB>
-int launch_fwd_rows(const void *feat, const int *shape, const int *start, const float *loc,
-                    const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
+// Channel split of the last wave.  The anchors of the last, partial wave of resident CTAs start only
+// when earlier anchors retire and then end the kernel (R50, bs=1: 900 anchors on 888 slots; the 12
+// late CTAs were the last to finish): they are split four ways by channels, which makes their CTAs a
+// quarter as long.  Measured: 19.2 -> 17.9 us at bs=1 / 900 anchors, 24.8 -> 23.5 us at 1220 anchors,
+// 31.6 -> 30.3 us at bs=2, neutral from bs=4 on.  DFA_FWD_SPLIT: 0 = never, 1 = as described
+// (default), 2 / 3 = every anchor two / four ways (experiments: par / slower).
+template <typename T>
+void last_wave_split(const Dims &d, int vpr, int ctas_per_sm, long long &split_from, int &split_log2,
+                     long long &grid) {
   constexpr int VEC = FeatVec<T>::VEC;
-  auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB>;
-  const int slices = NT / vpr;
-  int vpr_log2 = 0;
-  while ((1 << vpr_log2) < vpr) ++vpr_log2;
-  // Channel split.  The anchors of the last, partial wave of resident CTAs start only when earlier
-  // anchors retire and then end the kernel (R50, bs=1: 900 anchors on 888 slots; the 12 late CTAs
-  // were the last to finish): they are split four ways by channels, which makes their CTAs a quarter
-  // as long.  Measured: 19.2 -> 17.9 us at bs=1 / 900 anchors, 24.8 -> 23.5 us at 1220 anchors,
-  // 31.6 -> 30.3 us at bs=2, neutral from bs=4 on.  DFA_FWD_SPLIT: 0 = never, 1 = as described
-  // (default), 2 / 3 = every anchor two / four ways (experiments: par / slower).
   const long long total = static_cast<long long>(d.bs) * d.A;
-  long long split_from = total, grid = total;
-  int split_log2 = 0;
+  split_from = total, grid = total, split_log2 = 0;
   const int mode = env_int("DFA_FWD_SPLIT", 1);
   const int max_log2 = ((d.C / 4) % VEC == 0 && vpr >= 4) ? 2 : (((d.C / 2) % VEC == 0 && vpr >= 2) ? 1 : 0);
   if (mode == 1 && max_log2 == 2) {
@@ -1022,7 +1027,7 @@ int launch_fwd_rows(const void *feat, const int *shape, const int *start, const 
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
       if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-      const long long slots = static_cast<long long>(sm_count[dev]) * MINB;
+      const long long slots = static_cast<long long>(sm_count[dev]) * ctas_per_sm;
       const long long rem = slots > 0 ? total % slots : 0;  // anchors of the last, partial wave
       const int frac = env_int("DFA_FWD_SPLIT_FRAC", 2);  // split when the last wave is at most 1/frac full
       if (total > slots && rem > 0 && frac > 0 && rem <= slots / frac)
@@ -1031,6 +1036,18 @@ int launch_fwd_rows(const void *feat, const int *shape, const int *start, const 
   } else if (mode >= 2 && max_log2 >= mode - 1) {
     split_from = 0, split_log2 = mode - 1, grid = total << split_log2;
   }
+}
+
+template <typename T, int U, bool TMA, int NT, int MINB>
+int launch_fwd_rows(const void *feat, const int *shape, const int *start, const float *loc,
+                    const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
+  auto kern = dfa_fwd_rows_kernel<T, U, TMA, NT, MINB>;
+  const int slices = NT / vpr;
+  int vpr_log2 = 0;
+  while ((1 << vpr_log2) < vpr) ++vpr_log2;
+  long long split_from = 0, grid = 0;
+  int split_log2 = 0;
+  last_wave_split<T>(d, vpr, MINB, split_from, split_log2, grid);
   const int max_slices = slices << split_log2;
   SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C, slices, slices * U);
   const SmemLayout2 lay_s = smem_layout2(d.P, d.K, d.L, d.G, d.C >> split_log2, max_slices, max_slices * U);
@@ -1232,10 +1249,16 @@ int dfa_forward_fused(const void *mc_ms_feat, int feat_dtype, const int32_t *spa
     int vpr_log2 = 0;
     while ((1 << vpr_log2) < vpr) ++vpr_log2;
     auto kern = dfa_fwd_fused_kernel<T, NT, 6>;
-    const SmemLayoutF lay = smem_layout_fused(d.P, d.K, d.L, d.G, d.C, NT / vpr, NT);
+    long long split_from = 0, grid = 0;
+    int split_log2 = 0;
+    last_wave_split<T>(d, vpr, 6, split_from, split_log2, grid);
+    SmemLayoutF lay = smem_layout_fused(d.P, d.K, d.L, d.G, d.C, NT / vpr, NT);
+    const SmemLayoutF lay_s = smem_layout_fused(d.P, d.K, d.L, d.G, d.C >> split_log2, (NT / vpr) << split_log2, NT);
+    if (lay_s.total > lay.total) lay = lay_s;
     if (int rc = set_smem(kern, lay.total)) return rc;
-    kern<<<d.bs * d.A, NT, lay.total, st>>>(static_cast<const T *>(mc_ms_feat), spatial_shape,
-                                            scale_start_index, fa, output, d, vpr_log2);
+    kern<<<static_cast<unsigned int>(grid), NT, lay.total, st>>>(static_cast<const T *>(mc_ms_feat), spatial_shape,
+                                                                 scale_start_index, fa, output, d, vpr_log2,
+                                                                 static_cast<int>(split_from), split_log2);
     return static_cast<int>(cudaGetLastError());
   };
   if (feat_dtype == DFA_F32) return launch(float{});
