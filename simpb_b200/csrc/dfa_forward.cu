@@ -316,242 +316,6 @@ __global__ void __launch_bounds__(NT, MINB)
 
 
 // ------------------------------------------------------------------------------------------
-// forward, row-sliced mapping with helpers for heavy anchors (small grids)
-// ------------------------------------------------------------------------------------------
-// On a grid of about one wave the kernel ends with its heaviest anchors: an anchor with 26 valid
-// samples walks 26 dependent rounds of loads while the CTAs of light anchors have long retired
-// (profiles/r1_fwd_rows_timeline_bs1.txt).  Here an anchor with at least `heavy_min` valid samples
-// is processed in four channel blocks (quarter rows, four times the slices: the same rounds in total,
-// but in four independent pieces), and the pieces can be taken over by CTAs that have finished their
-// own anchor:
-//   * the owner publishes the anchor in a list in global memory, does block 0, then claims blocks
-//     1, 2, 3 one after the other (atomicOr on a per-anchor mask) and does those it gets;
-//   * a CTA that is done draws tickets from a global cursor; ticket t names (published anchor
-//     t % n, block 3 - t / n): it claims the block, stages the anchor's operands itself and computes
-//     and writes that block of channels.
-// Nobody waits for anybody (no spinning): every block is claimed by exactly one CTA, which computes
-// and stores it.  A block's bits do not depend on who computes it, and whether an anchor is heavy
-// depends on its own samples only, so the result is deterministic.  The list / mask / cursor live in
-// a ring of self-resetting slots (one per launch in flight), like the pooled kernel's ticket counter.
-constexpr int HELP_LCAP = 1024;  // published anchors per launch
-constexpr int HELP_SLOTS = 64;
-struct HelpState {
-  unsigned int reserve, cursor, exits, pad;
-  int list[HELP_LCAP];            // anchor + 1, 0 = not published
-  unsigned int claims[HELP_LCAP];  // bit p = channel block p taken
-};
-__device__ HelpState g_help[HELP_SLOTS];
-
-// One channel block of one anchor: gather with `slices` slices, fold the slices, store Cs channels.
-// Not inlined on purpose: the loop keeps the register allocation of the plain row-sliced kernel (four
-// loads in flight) whatever job state the caller carries.
-template <typename T, int NT>
-__device__ __noinline__ void help_gather_block(const unsigned char *fb, const uint4 *s_off, const float4 *s_bw,
-                                               const int *s_widx, const float *s_wg, float *s_red, int slice,
-                                               int chl, int ntaps_pad, int step, int Cs, int slices, float *outp) {
-  constexpr int VEC = FeatVec<T>::VEC;
-  float acc[VEC];
-#pragma unroll
-  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-  for (int t = slice; t < ntaps_pad; t += step) {
-    typename FeatVec<T>::raw_t val[4];
-    const uint4 off = s_off[t];
-    val[0] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + off.x));
-    val[1] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + off.y));
-    val[2] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + off.z));
-    val[3] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + off.w));
-    const float4 bw = s_bw[t];
-    const float wgt = s_wg[s_widx[t]];
-    const float c0 = bw.x * wgt, c1 = bw.y * wgt, c2 = bw.z * wgt, c3 = bw.w * wgt;
-    FeatVec<T>::fma(acc, c0, val[0]);
-    FeatVec<T>::fma(acc, c1, val[1]);
-    FeatVec<T>::fma(acc, c2, val[2]);
-    FeatVec<T>::fma(acc, c3, val[3]);
-  }
-  float4 *r = reinterpret_cast<float4 *>(s_red + slice * Cs + chl);
-#pragma unroll
-  for (int c = 0; c < VEC / 4; ++c) r[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-  __syncthreads();
-  for (int c = threadIdx.x; c < Cs; c += NT) {
-    float sum = 0.f;
-    for (int sl = 0; sl < slices; ++sl) sum += s_red[sl * Cs + c];
-    outp[c] = sum;
-  }
-}
-
-template <typename T, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-    dfa_fwd_rows_help_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
-                             const int *__restrict__ start, const float *__restrict__ loc,
-                             const float *__restrict__ weights, float *__restrict__ out, Dims d,
-                             int vpr_log2_full, int split_from, int heavy_min, HelpState *hs) {
-  constexpr int VEC = FeatVec<T>::VEC;
-  constexpr int U = 1;
-  extern __shared__ __align__(128) unsigned char smem[];
-  // one layout for every mode: sized for the 4-way split (most slices, largest tap padding)
-  const int slices_max = NT >> (vpr_log2_full - 2);
-  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C >> 2, slices_max, slices_max * U);  // red: [slices][Cs]
-  float *s_w = reinterpret_cast<float *>(smem + lay.w);
-  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
-  uint4 *s_off = reinterpret_cast<uint4 *>(smem + lay.off);
-  float4 *s_bw = reinterpret_cast<float4 *>(smem + lay.bw);
-  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
-  int *s_list = reinterpret_cast<int *>(smem + lay.list);
-  int *s_tab = reinterpret_cast<int *>(smem + lay.tab);
-  float *s_red = reinterpret_cast<float *>(smem + lay.red);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
-  int *s_misc = reinterpret_cast<int *>(bars + 2);  // [0] n_valid, [1] job word, [2] claim result
-
-  const int tid = threadIdx.x;
-  const int PK = d.P * d.K, wcount = PK * d.L * d.G;
-  const uint32_t rb = static_cast<uint32_t>(d.C) * sizeof(T);
-
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    fence_mbar_init();
-  }
-  for (int i = tid; i < d.K * d.L; i += NT) {
-    s_tab[3 * i] = __ldg(shape + 2 * i);
-    s_tab[3 * i + 1] = __ldg(shape + 2 * i + 1);
-    s_tab[3 * i + 2] = __ldg(start + i);
-  }
-
-  // job 0: the CTA's own anchor (or its channel block of a last-wave anchor); later jobs: help
-  int anchor = blockIdx.x, part_lo = 0, part_hi = 0;  // blocks [part_lo, part_hi] of a 4-way split; -1 = whole rows
-  bool presplit = false;
-  if (static_cast<int>(blockIdx.x) >= split_from) {
-    const int r = blockIdx.x - split_from;
-    anchor = split_from + (r >> 2);
-    part_lo = part_hi = r & 3;
-    presplit = true;
-  }
-  int my_pub = -1;  // index of the own anchor in the published list
-  for (int job = 0;; ++job) {
-    const uint32_t par = job & 1;
-    if (job > 0) {  // draw a ticket
-      if (tid == 0) {
-        int word = -1;
-        const unsigned int n = min(atomicAdd(&hs->reserve, 0u), static_cast<unsigned int>(HELP_LCAP));
-        for (;;) {
-          const unsigned int t = atomicAdd(&hs->cursor, 1u);
-          if (n == 0 || t >= 3u * n) break;
-          const unsigned int h = t % n, p = 3u - t / n;
-          const int a = *reinterpret_cast<volatile int *>(&hs->list[h]);
-          if (a == 0) continue;
-          if (atomicOr(&hs->claims[h], 1u << p) & (1u << p)) continue;
-          word = ((a - 1) << 2) | static_cast<int>(p);
-          break;
-        }
-        s_misc[1] = word;
-      }
-      __syncthreads();
-      const int word = s_misc[1];
-      if (word < 0) break;
-      anchor = word >> 2, part_lo = part_hi = word & 3;
-    }
-    const int b = anchor / d.A;
-    if (tid == 0) {
-      if (job > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&bars[0], 8u * PK);
-      tma_bulk_g2s(s_loc, loc + static_cast<size_t>(anchor) * PK * 2, 8u * PK, &bars[0]);
-      mbar_expect_tx(&bars[1], 4u * wcount);
-      tma_bulk_g2s(s_w, weights + static_cast<size_t>(anchor) * wcount, 4u * wcount, &bars[1]);
-    }
-    __syncthreads();  // barriers initialised / tables stored (job 0)
-    if (tid < 32) {
-      mbar_wait(&bars[0], par);
-      int n = 0;
-      for (int base = 0; base < PK; base += 32) {
-        const int s = base + tid;
-        bool v = false;
-        if (s < PK) v = sample_valid(s_loc[2 * s], s_loc[2 * s + 1]);
-        const unsigned m = __ballot_sync(0xffffffffu, v);
-        if (v) s_list[n + __popc(m & ((1u << tid) - 1u))] = s;
-        n += __popc(m);
-      }
-      if (tid == 0) s_misc[0] = n;
-    }
-    __syncthreads();
-    const int nv = s_misc[0];
-    const int ntaps = nv * d.L;
-    // mode of this job
-    int split_log2 = 2;
-    if (job == 0 && !presplit) {
-      if (heavy_min > 0 && nv >= heavy_min) {
-        part_lo = 0, part_hi = 3;
-        if (tid == 0) {
-          const unsigned int i = atomicAdd(&hs->reserve, 1u);
-          if (i < static_cast<unsigned int>(HELP_LCAP)) {
-            atomicOr(&hs->claims[i], 1u);  // block 0 is the owner's
-            __threadfence();
-            *reinterpret_cast<volatile int *>(&hs->list[i]) = anchor + 1;
-            my_pub = static_cast<int>(i);
-          }
-        }
-      } else {
-        split_log2 = 0, part_lo = part_hi = 0;
-      }
-    }
-    const int vpr_log2 = vpr_log2_full - split_log2;
-    const int vpr = 1 << vpr_log2, slices = NT >> vpr_log2;
-    const int Cs = d.C >> split_log2;
-    const int step = slices * U;
-    const int ntaps_pad = (ntaps + step - 1) / step * step;
-    for (int t = tid; t < ntaps_pad; t += NT) {
-      const int tt = t < ntaps ? t : 0;
-      const int l = tt / nv, i = tt - l * nv;  // level-major
-      const int s = s_list[i];
-      const int kl = (s % d.K) * d.L + l;
-      TapGeom gm;
-      tap_geometry(s_loc[2 * s], s_loc[2 * s + 1], s_tab[3 * kl], s_tab[3 * kl + 1], s_tab[3 * kl + 2], gm);
-      const int safe = gm.row[0] >= 0 ? gm.row[0] : gm.row[1] >= 0 ? gm.row[1]
-                     : gm.row[2] >= 0 ? gm.row[2] : gm.row[3];
-      const float live = t < ntaps ? 1.f : 0.f;
-      uint4 off;
-      float4 bw;
-      off.x = (gm.row[0] >= 0 ? gm.row[0] : safe) * rb, bw.x = gm.row[0] >= 0 ? live * gm.hh * gm.hw : 0.f;
-      off.y = (gm.row[1] >= 0 ? gm.row[1] : safe) * rb, bw.y = gm.row[1] >= 0 ? live * gm.hh * gm.lw : 0.f;
-      off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, bw.z = gm.row[2] >= 0 ? live * gm.lh * gm.hw : 0.f;
-      off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, bw.w = gm.row[3] >= 0 ? live * gm.lh * gm.lw : 0.f;
-      s_off[t] = off, s_bw[t] = bw, s_widx[t] = (s * d.L + l) * d.G;
-    }
-    __syncthreads();
-    mbar_wait(&bars[1], par);  // weights have landed
-
-    const int slice = tid >> vpr_log2, v = tid & (vpr - 1);
-    const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
-                              static_cast<size_t>(b) * d.num_feat * d.C * sizeof(T);
-    for (int part = part_lo; part <= part_hi; ++part) {
-      if (part > part_lo) {  // the owner of a heavy anchor: take the next block unless a helper has it
-        if (tid == 0)
-          s_misc[2] = my_pub < 0 ? 0 : static_cast<int>(atomicOr(&hs->claims[my_pub], 1u << part) & (1u << part));
-        __syncthreads();
-        const int taken = s_misc[2];
-        __syncthreads();
-        if (taken) continue;
-      }
-      const int ch_base = part * Cs;
-      const int ch = ch_base + v * VEC;
-      help_gather_block<T, NT>(fb + static_cast<uint32_t>(ch) * sizeof(T), s_off, s_bw, s_widx,
-                               s_w + ch / (d.C / d.G), s_red, slice, v * VEC, ntaps_pad, step, Cs, slices,
-                               out + static_cast<size_t>(anchor) * d.C + ch_base);
-      __syncthreads();  // s_red is rewritten by the next block / job
-    }
-    if (heavy_min <= 0) break;  // helping is off
-  }
-  if (tid == 0) {  // the last CTA out re-arms the slot
-    __threadfence();
-    if (atomicAdd(&hs->exits, 1u) == gridDim.x - 1) {
-      const unsigned int n = min(hs->reserve, static_cast<unsigned int>(HELP_LCAP));
-      for (unsigned int i = 0; i < n; ++i) hs->list[i] = 0, hs->claims[i] = 0u;
-      hs->reserve = 0u, hs->cursor = 0u, hs->exits = 0u;
-      __threadfence();
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // fused module forward: key points + projection + softmax of the attention logits + gather
 // ------------------------------------------------------------------------------------------
 // The row-sliced kernel with the module's front end folded into its prologue (inference): instead
@@ -1295,41 +1059,6 @@ int launch_fwd_rows(const void *feat, const int *shape, const int *start, const 
   return static_cast<int>(cudaGetLastError());
 }
 
-template <typename T, int NT, int MINB>
-int launch_fwd_rows_help(const void *feat, const int *shape, const int *start, const float *loc,
-                         const float *w, float *out, const Dims &d, int vpr, cudaStream_t st) {
-  static std::atomic<unsigned int> next_slot{0};
-  static HelpState *base[64] = {nullptr};
-  static std::mutex mu;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (!base[dev]) {
-      void *p = nullptr;
-      if (cudaGetSymbolAddress(&p, g_help) != cudaSuccess) return -1;
-      base[dev] = static_cast<HelpState *>(p);
-    }
-  }
-  if (vpr < 4 || (d.C / 4) % FeatVec<T>::VEC != 0) return -1;
-  auto kern = dfa_fwd_rows_help_kernel<T, NT, MINB>;
-  int vpr_log2 = 0;
-  while ((1 << vpr_log2) < vpr) ++vpr_log2;
-  long long split_from = 0, grid = 0;
-  int split_log2 = 0;
-  last_wave_split<T>(d, vpr, MINB, split_from, split_log2, grid);
-  if (split_log2 != 0 && split_log2 != 2) return -1;
-  const int slices_max = (NT / vpr) << 2;
-  const SmemLayout2 lay = smem_layout2(d.P, d.K, d.L, d.G, d.C >> 2, slices_max, slices_max);
-  if (set_smem(kern, lay.total)) return -1;
-  const int heavy_min = env_int("DFA_FWD_HEAVY_MIN", 18);
-  HelpState *hs = base[dev] + next_slot.fetch_add(1) % HELP_SLOTS;
-  kern<<<static_cast<unsigned int>(grid), NT, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
-                                                               out, d, vpr_log2, static_cast<int>(split_from),
-                                                               heavy_min, hs);
-  return static_cast<int>(cudaGetLastError());
-}
-
 // Row-sliced fast path: the row is a power-of-two number of 16-byte vectors (<= block size) and
 // every vector lies inside one channel group.
 template <typename T>
@@ -1405,19 +1134,14 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   }
   const int rvariant = variant >= 10 ? 1 : variant;
   if (rvariant >= 1) {
-    const int nt = (rvariant == 3 || rvariant == 4) ? 512 : 256;
+    const int nt = rvariant >= 3 ? 512 : 256;
     const int vpr = rows_vpr<T>(d, feat, nt);
     if (vpr) {
       const bool tma = tma_ok(d, loc, w);
 #define ROWS(U, NT, MINB)                                                                        \
   (tma ? launch_fwd_rows<T, U, true, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st)        \
        : launch_fwd_rows<T, U, false, NT, MINB>(feat, shape, start, loc, w, out, d, vpr, st))
-      if (rvariant == 7 && tma) {  // helpers for heavy anchors (small grids)
-        const int rc = launch_fwd_rows_help<T, 256, 6>(feat, shape, start, loc, w, out, d, vpr, st);
-        if (rc >= 0) return rc;
-      }
       switch (rvariant) {
-        case 7:
         case 1: return ROWS(1, 256, 6);
         case 2: return ROWS(2, 256, 4);
         case 3: return ROWS(1, 512, 3);
