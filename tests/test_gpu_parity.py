@@ -181,6 +181,22 @@ def test_forward_channel_split(anchors, monkeypatch):
         assert torch.equal(outs["1"][:, :888], outs["0"][:, :888])      # 148 SMs x 6 CTAs
 
 
+@pytest.mark.parametrize("mode", ["2", "3"])
+def test_forward_channel_split_small_shapes(mode, monkeypatch):
+    """Channel-split CTAs on shapes other than SimPB's (forced for every anchor): channels per block
+    down to one 16-byte vector, 1..16 groups, ragged levels, no-TMA operand sizes; shapes the split
+    does not fit must fall back silently."""
+    monkeypatch.setenv("DFA_FWD_SPLIT", mode)
+    cfgs = [dict(bs=2, A=7, P=5, K=3, sizes=SIZES3, C=32, G=2), dict(bs=1, A=9, P=4, K=2, sizes=SIZES3, C=64, G=8),
+            dict(bs=1, A=5, P=13, K=6, sizes=SIZES3, C=128, G=4), dict(bs=2, A=3, P=3, K=3, sizes=SIZES3, C=256, G=8),
+            dict(bs=1, A=4, P=6, K=2, sizes=SIZES3, C=512, G=16), dict(bs=1, A=6, P=2, K=2, sizes=SIZES3, C=16, G=1),
+            dict(bs=1, A=3, P=7, K=5, sizes=((5, 7),), C=48, G=3), dict(bs=1, A=2, P=40, K=6, sizes=SIZES3, C=256, G=8)]
+    for i, cfg in enumerate(cfgs):
+        d = small_case(700 + i, **cfg)
+        check_case(d, backward=False)
+        check_case(d, dtype=torch.bfloat16, backward=False)
+
+
 @pytest.mark.parametrize("variant", [20, 21, 22])
 def test_pooled_forward_schedules(variant, monkeypatch):
     """SM-pooled forward (DFA_FWD_VARIANT 20..22): every batch schedule — even split, static
