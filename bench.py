@@ -150,10 +150,15 @@ def time_graph(fn_list, steps, warmup, use_graph, sync_all, finalize=None):
         stream.synchronize()
         graph = None
         if use_graph:
+            if finalize is not None:
+                finalize()      # events recorded by the warm-up steps must not leak into the capture
+                stream.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 for f in fn_list:
                     f()
+                if finalize is not None:
+                    finalize()  # side streams forked inside the capture (all-reduce) join it here
             graph.replay()
             stream.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -313,7 +318,11 @@ def run_own_arm(args):
             return f
         fns = [mk(i, g, o) for i, (g, o) in enumerate(zip(sets, outs))]
 
-    use_graph = not args.no_graph and not (args.workload == "train" and dist is not None)
+    # The NCCL all-reduce is captured into the CUDA graph with the kernels (one launch per replay
+    # instead of ~20 eager launches per step); DFA_BENCH_EAGER_DIST=1 keeps the multi-GPU training
+    # step eager.
+    use_graph = not args.no_graph and not (args.workload == "train" and dist is not None
+                                           and os.environ.get("DFA_BENCH_EAGER_DIST") == "1")
     with ClockSampler(local) as clk:
         total_ms = time_graph(fns, args.steps, args.warmup, use_graph, sync_all, finalize)
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
