@@ -222,6 +222,52 @@ def module_case(blocks, name, seed, bs, A, embed, groups, sizes, cams, n_learn, 
     print(name, out.shape, sorted(dfa.state_dict().keys()))
 
 
+def op_full_size_case(blocks, ops, name, seed):
+    """BASELINE.json config #1 at full size: the reference's grid_sample path (`feature_sampling` +
+    `multi_view_level_fusion`, with the op's mask multiplied in) at the SimPB R50 704x256 shape —
+    bs=1, 6 cameras, 4 levels, 900 anchors, 13 key points, 256 channels / 8 groups — on the seeded
+    camera-rig inputs the benchmark uses (simpb_b200.synthetic.rig_op_inputs).  Only the output is
+    stored (0.9 MB); the inputs are regenerated from the seed by the test."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from simpb_b200 import synthetic
+    d = synthetic.rig_op_inputs(bs=1, seed=seed)
+    maps = ops.feature_maps_format([d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"]],
+                                   inverse=True)[0]
+    loc, w = d["sampling_location"], d["weights"]                       # [1,A,P,K,2], [1,A,P,K,L,G]
+    bs, A, P, K, _ = loc.shape
+    L, G = w.shape[4:6]
+    C = d["mc_ms_feat"].shape[-1]
+    w_klp = w.permute(0, 1, 3, 4, 2, 5).contiguous()                    # [1,A,K,L,P,G] (blocks.py:133-144 inverse)
+    dfa = make_dfa(blocks, C, G, L, K, 0, [[0, 0, 0]] * P, False, "add")
+    # gradients too (autograd through the reference path, one camera at a time to bound memory);
+    # the two large ones are stored as reductions: grad_weights summed over (p,k,l) per (anchor,
+    # group), grad_feat summed over the pixels of every (camera, level) per channel
+    maps = [m.requires_grad_() for m in maps]
+    loc = loc.clone().requires_grad_()
+    w_klp = w_klp.requires_grad_()
+    go = d["grad_output"]
+    total = 0
+    for k in range(K):
+        kp = torch.cat([loc[:, :, :, k], torch.ones_like(loc[:, :, :, k, :1])], -1)
+        proj = torch.eye(4)[None, None].repeat(bs, K, 1, 1)
+        f = blocks.DeformableFeatureAggregation.feature_sampling(maps, kp, proj, None)
+        x, y = loc[:, :, :, k, 0], loc[:, :, :, k, 1]
+        m = ((x > 0) & (x < 1) & (y > 0) & (y < 1)).float()          # op mask, .cu:168-171
+        f = f * m[:, :, None, None, :, None]
+        sel = torch.zeros(K)
+        sel[k] = 1
+        part = dfa.multi_view_level_fusion(f, w_klp * sel[None, None, :, None, None, None]).sum(dim=2)
+        part.backward(go)                                            # linear in `part`: per-camera backward
+        total = total + part.detach()
+    gw = w_klp.grad.permute(0, 1, 4, 2, 3, 5)                            # [1,A,P,K,L,G]
+    gfeat = torch.stack([torch.stack([mp.grad[0, k].sum(dim=(1, 2)) for mp in maps]) for k in range(K)])  # [K,L,C]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), out=total.numpy(), seed=np.int64(seed),
+                        grad_loc=loc.grad.numpy(), grad_weights_sum=gw.sum(dim=(2, 3, 4)).numpy(),
+                        grad_feat_level_sum=gfeat.numpy())
+    print(name, "out", total.shape, "abs max", float(total.abs().max()), "grad_loc abs max",
+          float(loc.grad.abs().max()))
+
+
 if __name__ == "__main__":
     blocks, ops = import_reference()
     sizes = [(8, 12), (4, 6), (2, 3)]
@@ -233,5 +279,6 @@ if __name__ == "__main__":
     op_case(blocks, "op_inner_f64", 4, 1, 9, 4, 2, sizes, 64, 8, 0.26, 0.74, False, torch.float64)
     module_case(blocks, "module_cat_cam", 5, bs=2, A=11, embed=64, groups=4, sizes=sizes, cams=3,
                 n_learn=2, camera_embed=True, residual="cat")
+    op_full_size_case(blocks, ops, "op_r50_rig_full", 77)
     module_case(blocks, "module_add_nocam", 6, bs=1, A=6, embed=32, groups=2, sizes=sizes, cams=2,
                 n_learn=0, camera_embed=False, residual="add")

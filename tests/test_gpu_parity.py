@@ -132,6 +132,29 @@ def test_r50_shape_uniform_vs_oracle():
     check_case(synthetic.op_inputs_uniform(bs=1, seed=0))
 
 
+def test_r50_full_size_vs_reference_fallback_fixture():
+    """The CUDA op (default dispatch, fp32 and bf16 tables) against the reference's own grid_sample
+    path at the benchmark shape: tests/golden/op_r50_rig_full.npz holds the reference output for the
+    seeded rig inputs (generated by tests/golden/make_golden.py from the unmodified reference)."""
+    from simpb_b200 import cabi, synthetic
+    gold = load_golden("op_r50_rig_full")
+    d = synthetic.rig_op_inputs(bs=1, seed=int(gold["seed"]))
+    g = dev(d)
+    out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    assert_close(out, gold["out"], RTOL_F32, "R50 full size vs reference fallback")
+    outh = cabi.forward(g["feat"].bfloat16(), g["shape"], g["start"], g["loc"], g["w"])
+    assert_close(outh, gold["out"], RTOL_BF16, "R50 full size, bf16 table, vs reference fallback")
+    # the three gradients (the two large ones through the reductions the fixture stores)
+    gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    assert_close(gl, gold["grad_loc"], 5 * RTOL_F32, "R50 full size grad_loc")
+    assert_close(gw.sum(dim=(2, 3, 4)), gold["grad_weights_sum"], RTOL_F32, "R50 full size grad_weights (sums)")
+    shape, start = d["spatial_shape"], d["scale_start_index"]
+    sums = torch.stack([torch.stack([gf[0, int(start[k, l]):int(start[k, l]) + int(shape[k, l, 0] * shape[k, l, 1])]
+                                     .double().sum(dim=0) for l in range(start.shape[1])])
+                        for k in range(start.shape[0])])
+    assert_close(sums, gold["grad_feat_level_sum"], RTOL_F32, "R50 full size grad_feat (sums)")
+
+
 def test_r50_shape_rig_vs_oracle():
     from simpb_b200 import synthetic
     check_case(synthetic.rig_op_inputs(bs=2, seed=3))
