@@ -268,6 +268,36 @@ def op_full_size_case(blocks, ops, name, seed):
           float(loc.grad.abs().max()))
 
 
+def module_released_case(blocks, name, seed, n_keep=48):
+    """The released SimPB+ R50 configuration (projects/configs/simpb_nus_r50_img_704x256.py:216-239:
+    256 channels, 8 groups, 4 levels, 6 cameras, 7 fixed + 6 learnable key points, camera embedding,
+    residual "cat") at full size — bs=1, 900 anchors, R50 704x256 maps, camera-rig inputs from
+    simpb_b200.synthetic.module_inputs_rig(seed).  Parameters come from tests/helpers.seeded_state_dict
+    (a 1 MB checkpoint would not be a small fixture), inputs are regenerated from the seed; stored are the
+    reference module's key points and, for the first n_keep anchors, its projected points, attention
+    weights and output (grid_sample path)."""
+    root = os.path.dirname(os.path.dirname(OUT))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    from simpb_b200 import synthetic
+    from helpers import seeded_state_dict
+    dfa = make_dfa(blocks, 256, 8, 4, 6, 6, FIX7, True, "cat")
+    dfa.load_state_dict(seeded_state_dict(dfa, seed))
+    dfa.eval()
+    d = synthetic.module_inputs_rig(bs=1, seed=seed)
+    metas = dict(projection_mat=d["projection_mat"], image_wh=d["image_wh"])
+    with torch.no_grad():
+        out = dfa(d["instance_feature"], d["anchor"], d["anchor_embed"], d["feature_maps"], metas)
+        kp = dfa.kps_generator(d["anchor"], d["instance_feature"])
+        w = dfa._get_weights(d["instance_feature"], d["anchor_embed"], metas)
+        uv = dfa.project_points(kp, d["projection_mat"], d["image_wh"])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=np.int64(seed), n_keep=np.int64(n_keep),
+                        key_points=kp.numpy(), points_2d=uv[:, :, :n_keep].numpy(),
+                        weights=w[:, :n_keep].numpy(), out=out[:, :n_keep].numpy(),
+                        out_abs_max=np.float64(out.abs().max()))
+    print(name, "out", out.shape, "abs max", float(out.abs().max()), "weights", w.shape)
+
+
 if __name__ == "__main__":
     blocks, ops = import_reference()
     sizes = [(8, 12), (4, 6), (2, 3)]
@@ -280,5 +310,6 @@ if __name__ == "__main__":
     module_case(blocks, "module_cat_cam", 5, bs=2, A=11, embed=64, groups=4, sizes=sizes, cams=3,
                 n_learn=2, camera_embed=True, residual="cat")
     op_full_size_case(blocks, ops, "op_r50_rig_full", 77)
+    module_released_case(blocks, "module_released_r50", 88)
     module_case(blocks, "module_add_nocam", 6, bs=1, A=6, embed=32, groups=2, sizes=sizes, cams=2,
                 n_learn=0, camera_embed=False, residual="add")

@@ -43,3 +43,25 @@ def golden_op_inputs(g):
     gmaps = [torch.from_numpy(g["grad_map%d" % l]) for l in range(n_levels)]
     gcol, _, _ = module_ref.flatten_feature_maps(gmaps)
     return col, shape, start, gcol
+
+
+def seeded_state_dict(module, seed):
+    """Deterministic parameters for a module whose checkpoint would be too large to commit: every
+    floating-point entry of the state dict, in sorted key order, is drawn from one seeded generator
+    (N(0,1) scaled by 1/sqrt(fan_in) for matrices, 1 + 0.1 N(0,1) for LayerNorm gains, 0.1 N(0,1) for
+    other vectors); buffers such as fix_scale are left alone.  The golden generator and the tests both
+    call this, so only the seed has to be stored."""
+    gen = torch.Generator().manual_seed(int(seed))
+    sd = module.state_dict()
+    out = {}
+    for k in sorted(sd):
+        v = sd[k]
+        if not v.is_floating_point() or k.endswith("fix_scale"):
+            out[k] = v.clone()
+        elif v.dim() >= 2:
+            out[k] = torch.randn(v.shape, generator=gen) / float(v.shape[-1]) ** 0.5
+        elif v.dim() == 1 and k.endswith("weight"):
+            out[k] = 1.0 + 0.1 * torch.randn(v.shape, generator=gen)
+        else:
+            out[k] = 0.1 * torch.randn(v.shape, generator=gen)
+    return out

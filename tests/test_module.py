@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import module_ref
-from helpers import RTOL_F32, assert_close, load_golden
+from helpers import RTOL_F32, assert_close, load_golden, seeded_state_dict
 
 GOLDEN = ["module_cat_cam", "module_add_nocam"]
 
@@ -155,6 +155,40 @@ def test_module_forward_matches_masked_reference_path(name):
         want = ref(tc["instance_feature"], tc["anchor"], tc["anchor_embed"], maps_c,
                    tc["projection_mat"], tc["image_wh"])
     assert_close(out, want, RTOL_F32, "module output")
+
+
+@pytest.mark.gpu
+def test_released_config_full_size_matches_the_reference_module():
+    """Released SimPB+ R50 configuration at full size on the GPU (fused inference kernel and the
+    three-kernel path): sampling locations and attention weights against the tensors of the unmodified
+    reference module (tests/golden/module_released_r50.npz), the module output against the masked
+    grid_sample restatement, which the CPU suite pins to the same fixture."""
+    from simpb_b200 import blocks, feature_maps_format, synthetic
+    from test_oracle_golden import RELEASED, released_ref
+    g = load_golden("module_released_r50")
+    n, seed = int(g["n_keep"]), int(g["seed"])
+    m = blocks.DeformableFeatureAggregation(
+        embed_dims=256, num_groups=8, num_levels=4, num_cams=6, attn_drop=0.15, use_deformable_func=True,
+        use_camera_embed=True, residual_mode="cat",
+        kps_generator=dict(type="SparseBox3DKeyPointsGenerator", num_learnable_pts=6, fix_scale=RELEASED["fix_scale"]))
+    m.load_state_dict(seeded_state_dict(m, seed))
+    m = m.cuda().eval()
+    d = synthetic.module_inputs_rig(bs=1, seed=seed)
+    t = {k: v.cuda() for k, v in d.items() if isinstance(v, torch.Tensor)}
+    metas = dict(projection_mat=t["projection_mat"], image_wh=t["image_wh"])
+    with torch.no_grad():
+        loc, w = m.sampling_and_weights(t["instance_feature"], t["anchor"], t["anchor_embed"], metas)
+        out = m(t["instance_feature"], t["anchor"], t["anchor_embed"],
+                feature_maps_format([x.cuda() for x in d["feature_maps"]]), metas)
+        want = released_ref(seed, "grid_sample_masked")(
+            d["instance_feature"], d["anchor"], d["anchor_embed"], d["feature_maps"], d["projection_mat"],
+            d["image_wh"])
+    ref_w = torch.from_numpy(g["weights"]).permute(0, 1, 4, 2, 3, 5)          # [1,n,P,K,L,G]
+    assert_close(w[:, :n], ref_w, RTOL_F32, "weights")
+    ref_uv = torch.from_numpy(g["points_2d"]).permute(0, 2, 3, 1, 4)          # [1,n,P,K,2]
+    sel = (ref_uv.abs() < 4).all(-1)
+    assert (loc[:, :n].cpu() - ref_uv)[sel].abs().max() < 1e-4
+    assert_close(out, want, RTOL_F32, "module output, released config")
 
 
 @pytest.mark.gpu
