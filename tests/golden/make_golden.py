@@ -208,9 +208,20 @@ def module_case(blocks, name, seed, bs, A, embed, groups, sizes, cams, n_learn, 
         kp = dfa.kps_generator(anchor, inst)
         w = dfa._get_weights(inst, emb, metas)
         uv = dfa.project_points(kp, proj, wh)
+    # training mode: the reference draws its attn-drop mask with torch.rand on the CPU generator
+    # (models/blocks.py:188-195); the same draw is repeated here and stored so that tests can inject it
+    dfa.train()
+    torch.manual_seed(seed + 2)
+    with torch.no_grad():
+        w_train = dfa._get_weights(inst, emb, metas)
+    dfa.eval()
+    torch.manual_seed(seed + 2)
+    keep = torch.rand(bs, A, cams, 1, w.shape[4], 1) > 0.15
+    assert torch.equal(w_train, (keep * w) / (1 - 0.15)), "mask replay does not match the reference draw"
     d = dict(instance_feature=inst.numpy(), anchor_embed=emb.numpy(), anchor=anchor.numpy(),
              projection_mat=proj.numpy(), image_wh=wh.numpy(), out=out.numpy(),
              key_points=kp.numpy(), weights=w.numpy(), points_2d=uv.numpy(),
+             train_weights=w_train.numpy(), train_keep=keep[:, :, :, 0, :, 0].numpy().astype(np.uint8),
              sizes=np.array(sizes, np.int64),
              cfg=np.array([embed, groups, len(sizes), cams, n_learn, int(camera_embed),
                            int(residual == "cat")], np.int64))

@@ -158,6 +158,24 @@ def test_module_forward_matches_masked_reference_path(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN)
+def test_training_mode_attn_drop_matches_reference_fixtures(name):
+    """Softmax + attn-drop + permute kernel in training mode against the weights the unmodified
+    reference module produced with the keep mask it drew (stored in the fixture)."""
+    g = load_golden(name)
+    m, sd = build_from_golden(g)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    t, _ = inputs(g, "cuda")
+    keep = torch.from_numpy(g["train_keep"]).cuda()
+    loc, w = m.sampling_and_weights(t["instance_feature"], t["anchor"], t["anchor_embed"],
+                                    dict(projection_mat=t["projection_mat"], image_wh=t["image_wh"]), keep=keep)
+    ref = torch.from_numpy(g["train_weights"]).permute(0, 1, 4, 2, 3, 5)      # [bs,A,P,K,L,G]
+    assert torch.equal(w.detach().cpu() == 0, ref == 0)
+    assert_close(w.detach(), ref, RTOL_F32, "training-mode weights")
+
+
+@pytest.mark.gpu
 def test_released_config_full_size_matches_the_reference_module():
     """Released SimPB+ R50 configuration at full size on the GPU (fused inference kernel and the
     three-kernel path): sampling locations and attention weights against the tensors of the unmodified
