@@ -378,6 +378,7 @@ int launch_fwd_pool(const void *feat, const int *shape, const int *start, const 
   const int pct = env_int("DFA_FWD_POOL_STATIC_PCT", 67);
   long long nb0 = total * pct / 100 / grid;
   nb0 = nb0 < 1 ? 1 : (nb0 > NB ? NB : nb0);
+  if (nb0 > total / grid) nb0 = total / grid;  // every CTA's static batch must exist (grid <= total)
   // a problem that fits one batch per CTA is dealt out evenly, no second iteration
   if (env_int("DFA_FWD_POOL_EVEN", 1) && (total + grid - 1) / grid <= NB) nb0 = 0;
   PoolArgs pa;
