@@ -2,7 +2,9 @@
 
 Two independent restatements of mmcv-full 1.7.1's `MultiScaleDeformableAttnFunction` (the reference
 calls it at projects/mmdet3d_plugin/models/group_attn.py:229-233; mmcv is not vendored and cannot be
-installed here, so parity is UNPINNED by reference vectors):
+installed here, so there are no vectors from mmcv itself; both restatements are pinned to a fixture
+from an independent third-party implementation of the same function, HuggingFace transformers'
+MultiScaleDeformableAttention — tests/golden/msda_hf.npz, tests/test_msda.py):
 
 * `forward` / `backward`: ctypes front-end of msda_oracle.c (mmcv's CUDA kernel, restated in C);
 * `msda_grid_sample`: mmcv's own CPU formulation `multi_scale_deformable_attn_pytorch`

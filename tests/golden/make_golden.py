@@ -309,6 +309,34 @@ def module_released_case(blocks, name, seed, n_keep=48):
     print(name, "out", out.shape, "abs max", float(out.abs().max()), "weights", w.shape)
 
 
+def msda_case(name, seed, bs, Q, M, D, sizes, P):
+    """Multi-scale deformable attention (the reference's 2-D branch calls mmcv-full 1.7.1's
+    MultiScaleDeformableAttnFunction, projects/mmdet3d_plugin/models/group_attn.py:229-233; mmcv is
+    not vendored and not installable here).  The fixture comes from an INDEPENDENT third-party
+    implementation of the same published function that this image does ship: HuggingFace transformers'
+    `MultiScaleDeformableAttention.forward` (Deformable-DETR's pure-PyTorch path, line for line the
+    algorithm of mmcv's `multi_scale_deformable_attn_pytorch`), forward and autograd gradients in fp64."""
+    from transformers.models.deformable_detr.modeling_deformable_detr import MultiScaleDeformableAttention
+    import transformers
+    g = torch.Generator().manual_seed(seed)
+    shapes = torch.tensor(sizes, dtype=torch.int64)
+    counts = shapes[:, 0] * shapes[:, 1]
+    start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]])
+    S, L = int(counts.sum()), len(sizes)
+    value = torch.randn(bs, S, M, D, generator=g)
+    loc = torch.rand(bs, Q, M, L, P, 2, generator=g) * 1.3 - 0.15
+    w = torch.rand(bs, Q, M, L, P, generator=g).reshape(bs, Q, M, -1).softmax(-1).reshape(bs, Q, M, L, P)
+    go = torch.randn(bs, Q, M * D, generator=g)
+    v64, l64, w64 = (t.double().requires_grad_() for t in (value, loc, w))
+    out = MultiScaleDeformableAttention()(v64, shapes, [tuple(x) for x in sizes], start, l64, w64, 64)
+    out.backward(go.double())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), value=value.numpy(), loc=loc.numpy(), w=w.numpy(),
+                        go=go.numpy(), sizes=np.array(sizes, np.int64), out=out.detach().numpy(),
+                        grad_value=v64.grad.numpy(), grad_loc=l64.grad.numpy(), grad_w=w64.grad.numpy(),
+                        transformers_version=np.array(transformers.__version__))
+    print(name, "out", out.shape, "abs max", float(out.abs().max()), "transformers", transformers.__version__)
+
+
 if __name__ == "__main__":
     blocks, ops = import_reference()
     sizes = [(8, 12), (4, 6), (2, 3)]
@@ -322,5 +350,6 @@ if __name__ == "__main__":
                 n_learn=2, camera_embed=True, residual="cat")
     op_full_size_case(blocks, ops, "op_r50_rig_full", 77)
     module_released_case(blocks, "module_released_r50", 88)
+    msda_case("msda_hf", 9, bs=2, Q=17, M=8, D=32, sizes=[(6, 10), (3, 5), (2, 3)], P=4)
     module_case(blocks, "module_add_nocam", 6, bs=1, A=6, embed=32, groups=2, sizes=sizes, cams=2,
                 n_learn=0, camera_embed=False, residual="add")

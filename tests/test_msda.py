@@ -1,13 +1,15 @@
 """Multi-scale deformable attention (the 2-D query branch's gather).  mmcv-full 1.7.1 is not
-vendored, so there are no reference vectors: the C oracle (mmcv's CUDA kernel restated) and the
-grid_sample formulation (mmcv's CPU fallback restated) are first checked against each other, then
-the CUDA kernels against the oracle."""
+vendored, so there are no vectors from mmcv itself: the C oracle (mmcv's CUDA kernel restated) and
+the grid_sample formulation (mmcv's CPU fallback restated) are checked against each other and against
+a fixture produced by an independent third-party implementation of the same published function
+(HuggingFace transformers' MultiScaleDeformableAttention, tests/golden/msda_hf.npz), then the CUDA
+kernels against the oracle and the fixture."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import msda_ref
-from helpers import RTOL_BF16, RTOL_F32, assert_close
+from helpers import RTOL_BF16, RTOL_F32, assert_close, load_golden
 
 SIZES3 = ((8, 12), (4, 6), (2, 3))
 
@@ -40,6 +42,42 @@ def test_c_oracle_matches_grid_sample_formulation(cfg):
     assert_close(gv, v.grad, 2e-6, "grad_value")
     assert_close(gw, w.grad, 2e-6, "grad_attn_weight")
     assert_close(gl, l.grad, 1e-5, "grad_sampling_loc")
+
+
+def hf_case():
+    g = load_golden("msda_hf")
+    shapes = torch.from_numpy(g["sizes"])
+    counts = shapes[:, 0] * shapes[:, 1]
+    start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]])
+    d = dict(value=torch.from_numpy(g["value"]), shapes=shapes, start=start, loc=torch.from_numpy(g["loc"]),
+             w=torch.from_numpy(g["w"]), go=torch.from_numpy(g["go"]))
+    return g, d
+
+
+def test_oracles_match_the_third_party_fixture():
+    """Forward and the three gradients of both restatements against HuggingFace transformers'
+    implementation (fp64 autograd), stored in tests/golden/msda_hf.npz; and, when transformers is
+    importable, against a live call on the same inputs."""
+    g, d = hf_case()
+    out = msda_ref.forward(d["value"], d["shapes"], d["start"], d["loc"], d["w"])
+    assert_close(out, g["out"], 2e-6, "C oracle forward")
+    gv, gl, gw = msda_ref.backward(d["value"], d["shapes"], d["start"], d["loc"], d["w"], d["go"])
+    assert_close(gv, g["grad_value"], 2e-6, "C oracle grad_value")
+    assert_close(gw, g["grad_w"], 2e-6, "C oracle grad_attn_weight")
+    assert_close(gl, g["grad_loc"], 1e-5, "C oracle grad_sampling_loc")
+    v, l, w = (d[k].double().requires_grad_() for k in ("value", "loc", "w"))
+    ref = msda_ref.msda_grid_sample(v, d["shapes"], l, w)
+    assert_close(ref, g["out"], 1e-12, "grid_sample restatement forward")
+    ref.backward(d["go"].double())
+    assert_close(v.grad, g["grad_value"], 1e-12, "grid_sample restatement grad_value")
+    assert_close(l.grad, g["grad_loc"], 1e-10, "grid_sample restatement grad_sampling_loc")
+    try:
+        from transformers.models.deformable_detr.modeling_deformable_detr import MultiScaleDeformableAttention
+    except Exception:
+        return
+    live = MultiScaleDeformableAttention()(d["value"].double(), d["shapes"], [tuple(x) for x in g["sizes"].tolist()],
+                                           d["start"], d["loc"].double(), d["w"].double(), 64)
+    assert_close(live, g["out"], 1e-12, "live transformers call")
 
 
 def test_taps_outside_the_border_band_contribute_nothing():
@@ -103,6 +141,21 @@ def check(d, dtype=torch.float32):
 ])
 def test_kernels_vs_oracle_small_shapes(cfg):
     check(make_case(3, **cfg))
+
+
+@pytest.mark.gpu
+def test_kernels_vs_third_party_fixture():
+    """CUDA forward / backward against the HuggingFace-transformers fixture."""
+    from simpb_b200 import cabi
+    g, d = hf_case()
+    c = {k: v.cuda() for k, v in d.items()}
+    shapes, start = c["shapes"].int(), c["start"].int()
+    out = cabi.msda_forward(c["value"], shapes, start, c["loc"], c["w"])
+    assert_close(out, g["out"], RTOL_F32, "msda forward")
+    gv, gl, gw = cabi.msda_backward(c["value"], shapes, start, c["loc"], c["w"], c["go"])
+    assert_close(gv, g["grad_value"], RTOL_F32, "grad_value")
+    assert_close(gw, g["grad_w"], RTOL_F32, "grad_attn_weight")
+    assert_close(gl, g["grad_loc"], 5 * RTOL_F32, "grad_sampling_loc")
 
 
 @pytest.mark.gpu
