@@ -1095,28 +1095,10 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   // 10..12 = row-merging kernel (fewer DRAM bytes and L1 wavefronts, longer dependent chain per
   // warp: within 5-25 % of the default); 0 = one-warp-per-group kernel.
   // A variant whose shape constraints are not met falls through to the next family.
-  // Default (no override): the row-sliced kernel; for bfloat16 tables, whose rows are half as long,
-  // two taps in flight per thread on small grids and the row-merging kernel on large ones measured
-  // 6-8 % faster (tools/sweep_fwd.py).
-  const bool big_grid = static_cast<long long>(d.bs) * d.A > 148 * 16;
-  const int variant = env_int("DFA_FWD_VARIANT", sizeof(T) == 2 ? (big_grid ? 11 : 2) : 1);
-  if (variant >= 10 && variant < 20) {  // merging kernel: (warps, rows in flight, CTAs per SM) per variant
-    const int vpl = merge_vpl<T>(d, feat);
-    if (vpl) {
-      const bool tma = warp_tma_ok(d, loc, w);
-#define WARPK(VPL, NW, U, MINB)                                                                  \
-  (tma ? launch_fwd_merge<T, VPL, NW, U, true, MINB>(feat, shape, start, loc, w, out, d, st)       \
-       : launch_fwd_merge<T, VPL, NW, U, false, MINB>(feat, shape, start, loc, w, out, d, st))
-#define WARPV(NW, U, MINB) (vpl == 2 ? WARPK(2, NW, U, MINB) : WARPK(1, NW, U, MINB))
-      switch (variant) {
-        case 11: return WARPV(4, 4, 8);
-        case 12: return WARPV(8, 4, 4);
-        default: return WARPV(4, 4, 10);
-      }
-#undef WARPV
-#undef WARPK
-    }
-  }
+  // Default (no override): the row-sliced kernel with one tap in flight per thread, for fp32 and
+  // bfloat16 tables alike (with the channel split of the last wave it also beats the earlier
+  // bfloat16 picks: 14.1 vs 15.3 us (variant 2) at bs=1, 71.9 vs 72.9 us (variant 11) at bs=8).
+  const int variant = env_int("DFA_FWD_VARIANT", 1);
   if (variant >= 20) {  // SM-pooled kernel: 20 = one 1024-thread CTA per SM, 21 = two 512-thread CTAs
     const int vpl = pool_vpl<T>(d, feat, loc, out);
     if (vpl) {
