@@ -113,6 +113,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1)
   const int total = d.bs * d.A;
   const int dyn0 = pa.nb0 == 0 ? total : gridDim.x * pa.nb0;  // anchors [0, dyn0): static first batches
 
+#ifdef DFA_PHASE_TIMING
+  if (g_phase_buf && tid == 0) {  // wall clock of the CTA's first instruction
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_phase_buf[(static_cast<size_t>(blockIdx.x) * 16 + 15) * 16 + 0] = static_cast<long long>(gt);
+  }
+#endif
   int cur_start = blockIdx.x * pa.nb0, cur_n = pa.nb0;
   if (pa.nb0 == 0) {
     cur_start = static_cast<int>(static_cast<long long>(blockIdx.x) * total / gridDim.x);
@@ -326,6 +333,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1)
     }
     cur_start = s_misc[2 * (st ^ 1)], cur_n = s_misc[2 * (st ^ 1) + 1];
   }
+#ifdef DFA_PHASE_TIMING
+  if (g_phase_buf && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_phase_buf[(static_cast<size_t>(blockIdx.x) * 16 + 15) * 16 + 1] = static_cast<long long>(gt);
+  }
+#endif
   if (pa.dynamic && pa.nb0 != 0 && tid == NT - 32) {  // (the drawing thread) the last CTA out re-arms the ticket slot
     __threadfence();
     const unsigned int prev = atomicAdd(&pa.sched[1], 1u);

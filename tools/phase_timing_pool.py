@@ -66,6 +66,12 @@ e1.record()
 torch.cuda.synchronize()
 print("event time of one more launch (stamped build): %.1f us" % (e0.elapsed_time(e1) * 1e3))
 t = buf.cpu().double()
+gt = buf.cpu()[:, 15, :2]
+gl = gt[:, 0] > 0
+if gl.any():
+    print("wall clock (globaltimer): CTA starts span %.2f us, first start to last end %.2f us, CTA life median %.2f / max %.2f us"
+          % ((gt[gl, 0].max() - gt[gl, 0].min()) / 1e3, (gt[gl, 1].max() - gt[gl, 0].min()) / 1e3,
+             float((gt[gl, 1] - gt[gl, 0]).double().median()) / 1e3, float((gt[gl, 1] - gt[gl, 0]).max()) / 1e3))
 names = {0: "iteration top", 10: "sched: next copy issued", 11: "loc landed (warp 0)",
          1: "compaction barrier", 2: "records barrier", 4: "gather done (warp 0)",
          5: "gather barrier", 6: "reduce done (thread 0)"}
