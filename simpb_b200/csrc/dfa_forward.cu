@@ -1098,7 +1098,12 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   // Default (no override): the row-sliced kernel with one tap in flight per thread, for fp32 and
   // bfloat16 tables alike (with the channel split of the last wave it also beats the earlier
   // bfloat16 picks: 14.1 vs 15.3 us (variant 2) at bs=1, 71.9 vs 72.9 us (variant 11) at bs=8).
-  const int variant = env_int("DFA_FWD_VARIANT", 1);
+  // With many potential taps per anchor (more key points than SimPB's 13: P*K*L >= 400) the chains
+  // of dependent load rounds are long enough that two taps in flight at 4 CTAs per SM win: 26.7 vs
+  // 32.0 us at 20 key points, 38.2 vs 42.2 us at 32 (900 anchors, fp32; bf16 and 1800 / 3600 anchors
+  // alike, 5-17 %); at 13 key points it is the other way round (17.9 vs 21.5 us).
+  const bool long_chains = static_cast<long long>(d.P) * d.K * d.L >= 400;
+  const int variant = env_int("DFA_FWD_VARIANT", long_chains ? 2 : 1);
   if (variant >= 20) {  // SM-pooled kernel: 20 = one 1024-thread CTA per SM, 21 = two 512-thread CTAs
     const int vpl = pool_vpl<T>(d, feat, loc, out);
     if (vpl) {
