@@ -1023,11 +1023,13 @@ void last_wave_split(const Dims &d, int vpr, int ctas_per_sm, long long &split_f
   const int mode = env_int("DFA_FWD_SPLIT", 1);
   const int max_log2 = ((d.C / 4) % VEC == 0 && vpr >= 4) ? 2 : (((d.C / 2) % VEC == 0 && vpr >= 2) ? 1 : 0);
   if (mode == 1 && max_log2 == 2) {
-    static int sm_count[64] = {0};
+    static std::atomic<int> sm_count[64];  // 0 = not queried yet; racing threads store the same value
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
-      if (!sm_count[dev]) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-      const long long slots = static_cast<long long>(sm_count[dev]) * ctas_per_sm;
+      int sms = sm_count[dev].load(std::memory_order_relaxed);
+      if (!sms && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+        sm_count[dev].store(sms, std::memory_order_relaxed);
+      const long long slots = static_cast<long long>(sms) * ctas_per_sm;
       const long long rem = slots > 0 ? total % slots : 0;  // anchors of the last, partial wave
       const int frac = env_int("DFA_FWD_SPLIT_FRAC", 2);  // split when the last wave is at most 1/frac full
       if (total > slots && rem > 0 && frac > 0 && rem <= slots / frac)
