@@ -980,6 +980,7 @@ __global__ void dfa_debug_indices_kernel(const int *__restrict__ shape, const in
 }  // namespace
 
 #include "dfa_forward_pool.cuh"
+#include "dfa_forward_win.cuh"
 
 namespace {
 
@@ -1088,6 +1089,30 @@ int launch_fwd_merge(const void *feat, const int *shape, const int *start, const
   return static_cast<int>(cudaGetLastError());
 }
 
+template <typename T, int VPL, bool TMA, int NW, int MINB>
+int launch_fwd_win(const void *feat, const int *shape, const int *start, const float *loc,
+                   const float *w, float *out, const Dims &d, cudaStream_t st) {
+  auto kern = dfa_fwd_win_kernel<T, VPL, TMA, NW, MINB>;
+  // A grid of about one wave is bound by latency: fetch the whole weights block with the locations
+  // instead of the valid samples' weights next to the row loads.
+  const long long grid = static_cast<long long>(d.bs) * d.A;
+  const int whole = TMA ? env_int("DFA_FWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0) : 0;
+  const int merge_pix = env_int("DFA_FWD_MERGE_PIX", WIN_MAP);
+  const WinLayout lay = win_layout(d.P, d.K, d.L, d.G, d.C, NW, whole != 0);
+  if (int rc = set_smem(kern, lay.total)) return rc;
+  // Channel split of the anchors that start last (see the kernel): DFA_FWD_TAIL_SPLIT = how many
+  // waves of resident CTAs, in tenths, run split at the end of the grid.
+  long long split_from = grid;
+  if (VPL == 2) {
+    const long long slots = 148ll * MINB;
+    const long long n = slots * env_int("DFA_FWD_TAIL_SPLIT", 10) / 10 / 2;  // anchors -> two CTAs each
+    if (grid > 2 * slots && n > 0) split_from = grid - n;
+  }
+  kern<<<static_cast<unsigned int>(split_from + 2 * (grid - split_from)), NW * 32, lay.total, st>>>(
+      static_cast<const T *>(feat), shape, start, loc, w, out, d, merge_pix, whole, static_cast<int>(split_from));
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <typename T>
 int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
                   const float *w, float *out, const Dims &d, cudaStream_t st) {
@@ -1106,7 +1131,7 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
   // alike, 5-17 %); at 13 key points it is the other way round (17.9 vs 21.5 us).
   const bool long_chains = static_cast<long long>(d.P) * d.K * d.L >= 400;
   const int variant = env_int("DFA_FWD_VARIANT", long_chains ? 2 : 1);
-  if (variant >= 20) {  // SM-pooled kernel: 20 = one 1024-thread CTA per SM, 21 = two 512-thread CTAs
+  if (variant >= 20 && variant < 30) {  // SM-pooled kernel: 20 = one 1024-thread CTA per SM, 21 = two 512-thread CTAs
     const int vpl = pool_vpl<T>(d, feat, loc, out);
     if (vpl) {
       int rc;
@@ -1119,6 +1144,24 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
       else rc = POOL(1024);
 #undef POOL
       if (rc >= 0) return rc;
+    }
+  }
+  if (variant >= 30 && variant < 40) {  // warp-autonomous window-merging kernel
+    const int vpl = win_vpl<T>(d, feat);
+    if (vpl) {
+      const bool tma = tma_ok(d, loc, w);
+#define WIN(NW, MINB)                                                                             \
+  (vpl == 2 ? (tma ? launch_fwd_win<T, 2, true, NW, MINB>(feat, shape, start, loc, w, out, d, st)    \
+                   : launch_fwd_win<T, 2, false, NW, MINB>(feat, shape, start, loc, w, out, d, st))  \
+            : (tma ? launch_fwd_win<T, 1, true, NW, MINB>(feat, shape, start, loc, w, out, d, st)    \
+                   : launch_fwd_win<T, 1, false, NW, MINB>(feat, shape, start, loc, w, out, d, st)))
+      switch (variant) {
+        case 31: return WIN(8, 4);
+        case 32: return WIN(4, 7);
+        case 33: return WIN(2, 16);
+        default: return WIN(4, 8);
+      }
+#undef WIN
     }
   }
   const int rvariant = variant >= 10 ? 1 : variant;

@@ -160,7 +160,7 @@ def test_r50_shape_rig_vs_oracle():
     check_case(synthetic.rig_op_inputs(bs=2, seed=3))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 10, 11, 12, 20, 21, 22])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 10, 11, 12, 20, 21, 22, 30, 31, 32, 33])
 def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
     """DFA_FWD_VARIANT selects the forward kernel family / tuning point; all of them must agree
     with the oracle (fp32 and bf16 feature tables, sparse rig and dense uniform locations)."""

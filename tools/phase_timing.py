@@ -57,24 +57,31 @@ for i in range(3):   # the last launch (cold inputs: 3 sets rotate) is the one a
 torch.cuda.synchronize()
 t = buf.cpu().double()
 t = t[t[:, 0, 0] > 0]       # CTAs that ran
-if a.variant < 10:     # row-sliced kernel: its own stamp meanings
+rows_like = a.variant < 10 or a.variant >= 30
+if a.variant >= 30:    # window-merging kernel
+    names = ["0 start", "1 locations landed, camera masks", "2 barrier (+ weights landed)", "3 fine-level taps done",
+             "4 coarse-level units done", "5 end", "-", "-"]
+elif a.variant < 10:     # row-sliced kernel: its own stamp meanings
     names = ["0 start", "1 operands staged + compaction", "2 tap records", "3 barrier + weights landed",
              "4 gather done", "5 end", "-", "-"]
 else:
     names = ["0 start", "1 loc landed / tables", "2 compaction+weights issued", "3 barrier A", "4 merge done",
              "5 barrier B", "6 gather done", "7 end"]
+if os.environ.get("PHASE_DEBUG"):
+    torch.set_printoptions(precision=0, linewidth=200, sci_mode=False)
+    print(t[0].long()); print(t[5].long()); print(t.shape)
 t0 = t[:, :, 0].min(dim=1, keepdim=True).values          # CTA start
 print("variant", a.variant, "batch", a.batch, "anchors", n_anchor)
 print("phase stamps relative to CTA start, cycles: median / p90 / max over (anchor, warp)")
-for i in range(1, 8):
+for i in range(1, 6 if rows_like else 8):
     x = (t[:, :, i] - t0).flatten()
     x = x[t[:, :, i].flatten() > 0]
     if x.numel():
         print("  %-30s %8.0f %8.0f %8.0f" % (names[i], x.median(), x.quantile(0.9), x.max()))
-last = 5 if a.variant < 10 else 7
+last = 5 if rows_like else 7
 life = (t[:, :, last].max(dim=1).values - t0[:, 0])
 print("CTA lifetime: median %.0f p90 %.0f max %.0f cycles" % (life.median(), life.quantile(0.9), life.max()))
-if a.variant < 10:     # globaltimer (ns) at CTA start / end: launch ramp and tail in wall time
+if rows_like:     # globaltimer (ns) at CTA start / end: launch ramp and tail in wall time
     gs, ge = t[:, 0, 6], t[:, :, 7].max(dim=1).values
     first = gs.min()
     print("wall clock (globaltimer, us): CTA starts  median %.2f  p90 %.2f  max %.2f   |   CTA ends  median %.2f  p90 %.2f  "
