@@ -7,8 +7,11 @@
  *   0                      success
  *   > 0                    a cudaError_t raised by the launch / runtime
  *   DFA_ERR_* (< 0)        argument validation failed — nothing was launched
- * Nothing throws across this boundary and the library keeps no global state, so it is
- * re-entrant from any host thread (PyTorch's autograd thread included).
+ * Nothing throws across this boundary and every entry point is re-entrant from any host thread
+ * (PyTorch's autograd thread included).  The only process-wide state is read-only after first use:
+ * the SM count of each device and the DFA_* tuning knobs, which are environment variables read once
+ * per process (tests and tools switch kernels with them; dfa_debug_reload_knobs() makes the library
+ * read them again).  No launch path calls getenv() after that.
  *
  * Reference interface each entry point replaces (paths under
  * /root/reference/projects/mmdet3d_plugin/):
@@ -76,6 +79,8 @@ typedef struct dfa_dims {
 } dfa_dims;
 
 int dfa_version(void);
+/* Tests / tools: re-read the DFA_* tuning environment variables on their next use. */
+void dfa_debug_reload_knobs(void);
 const char *dfa_error_string(int code);
 
 /* out[b,a,c] = sum_{p,k,l} valid(b,a,p,k) * w[b,a,p,k,l,c/(C/G)] * bilinear(feat, loc)  —

@@ -16,7 +16,7 @@ F32, BF16 = 0, 1
 BWD_ACCUMULATE, BWD_OVERWRITE_SMALL, BWD_ZERO_GRAD_FEAT = 0, 1, 2
 
 # every symbol include/dfa_b200.h declares (tests check the library exports each of them)
-SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_forward", "dfa_backward", "dfa_forward_fused",
+SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_debug_reload_knobs", "dfa_forward", "dfa_backward", "dfa_forward_fused",
            "dfa_debug_indices",
            "dfa_flatten_maps", "dfa_keypoints_project", "dfa_keypoints_project_backward",
            "dfa_softmax_weights", "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
@@ -44,6 +44,8 @@ def _load():
     lib.dfa_version.restype = i32
     lib.dfa_error_string.restype = ctypes.c_char_p
     lib.dfa_error_string.argtypes = [i32]
+    lib.dfa_debug_reload_knobs.restype = None
+    lib.dfa_debug_reload_knobs.argtypes = []
     lib.dfa_forward.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp]
     lib.dfa_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, dp, i32, vp]
     lib.dfa_forward_fused.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, dp, vp]
@@ -76,6 +78,12 @@ def _load():
 
 
 lib = _load()
+
+
+def reload_knobs():
+    """Tests / tools: the library caches its DFA_* tuning environment variables on first use; call this
+    after changing one of them."""
+    lib.dfa_debug_reload_knobs()
 
 
 def check(rc, what):
@@ -145,7 +153,10 @@ def forward(feat, shape, start, loc, w, out=None):
 def backward(feat, shape, start, loc, w, grad_out, grad_feat=None, grad_loc=None, grad_w=None,
              flags=None, need_feat=True):
     """With no buffers given: allocates them, lets the kernel write the two small gradients in full
-    and zero-fills grad_feat on the stream (one memset instead of the reference's three).
+    and zero-fills grad_feat on the stream (one memset instead of the reference's three).  With every
+    buffer given (and no flags): the reference contract, accumulate into caller-zeroed buffers.  A
+    caller that passes only SOME of the buffers must say what it wants with `flags` — guessing could
+    overwrite a buffer it expected to be accumulated into.
     need_feat=False skips the feature gradient (scatter and zero-fill) and returns None for it."""
     _need(feat, "mc_ms_feat"); _need(shape, "spatial_shape", torch.int32)
     _need(start, "scale_start_index", torch.int32)
@@ -156,6 +167,10 @@ def backward(feat, shape, start, loc, w, grad_out, grad_feat=None, grad_loc=None
         raise DfaError("grad_output must be [bs, anchors, embeds]")
     if flags is None:
         all_given = (grad_feat is not None or not need_feat) and grad_loc is not None and grad_w is not None
+        none_given = grad_feat is None and grad_loc is None and grad_w is None
+        if not (all_given or none_given):
+            raise DfaError("dfa_backward: some gradient buffers were passed and some were not; "
+                           "pass `flags` (BWD_ACCUMULATE or BWD_OVERWRITE_SMALL [| BWD_ZERO_GRAD_FEAT])")
         flags = BWD_ACCUMULATE if all_given else BWD_OVERWRITE_SMALL
         if grad_feat is None and need_feat:
             grad_feat = torch.empty(feat.shape, device=feat.device, dtype=torch.float32)

@@ -677,7 +677,7 @@ int launch_bwd_merge(const void *feat, const int *shape, const int *start, const
   const MergeBwdLayout lay = merge_bwd_layout(d.P, d.K, d.L, d.G, NW, U);
   if (int rc = set_smem(kern, lay.total)) return rc;
   const long long grid = static_cast<long long>(d.bs) * d.A;
-  const int whole = env_int("DFA_BWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0);
+  const int whole = DFA_KNOB("DFA_BWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0);
   kern<<<d.bs * d.A, NW * 32, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w, go,
                                               gf, gl, gw, d, lay, whole, overwrite);
   return static_cast<int>(cudaGetLastError());
@@ -689,7 +689,7 @@ int backward_typed(const void *feat, const int *shape, const int *start, const f
                    int overwrite, cudaStream_t st) {
   // DFA_BWD_VARIANT (tuning knob): 10.. = row-merging kernel (default where the shape fits),
   // 0 = one-warp-per-group kernel.
-  const int variant = env_int("DFA_BWD_VARIANT", 10);
+  const int variant = DFA_KNOB("DFA_BWD_VARIANT", 10);
   if (variant >= 10 && aligned(go, 16) && aligned(gf, 16)) {
     const int vpl = merge_vpl<T>(d, feat);
     const MergeBwdLayout bl = merge_bwd_layout(d.P, d.K, d.L, d.G, 8, 4);

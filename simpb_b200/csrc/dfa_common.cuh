@@ -13,7 +13,13 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "dfa_b200.h"
+
+// Generation of the tuning-knob cache (defined in dfa_forward.cu): dfa_debug_reload_knobs() bumps it
+// and every cached knob re-reads its environment variable on its next use.
+extern std::atomic<int> dfa_knob_generation;
 
 namespace {
 
@@ -376,10 +382,29 @@ inline bool tma_ok(const Dims &d, const float *loc, const float *w) {
   return wbytes % 16 == 0 && lbytes % 16 == 0 && aligned(loc, 16) && aligned(w, 16);
 }
 
-inline int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : dflt;
+// Tuning knobs (tests and tools only): an environment variable is read ONCE per call site and
+// process — not on every launch — and again only after dfa_debug_reload_knobs().  Racing host
+// threads compute the same value; nothing is read from the environment on the launch path afterwards.
+struct KnobCache {
+  std::atomic<int> gen{-1};
+  std::atomic<int> val{0};
+};
+constexpr int KNOB_UNSET = -0x7fffffff - 1;
+inline int knob_get(KnobCache &c, const char *name, int dflt) {
+  const int g = dfa_knob_generation.load(std::memory_order_relaxed);
+  if (c.gen.load(std::memory_order_acquire) != g) {
+    const char *e = getenv(name);
+    c.val.store(e ? atoi(e) : KNOB_UNSET, std::memory_order_relaxed);
+    c.gen.store(g, std::memory_order_release);
+  }
+  const int v = c.val.load(std::memory_order_relaxed);
+  return v == KNOB_UNSET ? dflt : v;
 }
+#define DFA_KNOB(name, dflt)        \
+  ([&]() -> int {                   \
+    static KnobCache cache_;        \
+    return knob_get(cache_, name, (dflt)); \
+  }())
 
 // The merging kernel applies when a feature row is 512 or 1024 bytes (a lane owns one or two
 // 16-byte vectors of it) and there are 8 channel groups — SimPB's C=256 / G=8 in fp32 and bf16.

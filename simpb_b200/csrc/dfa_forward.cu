@@ -13,6 +13,8 @@
 
 #include "dfa_common.cuh"
 
+std::atomic<int> dfa_knob_generation{0};
+
 namespace {
 
 #ifdef DFA_PHASE_TIMING
@@ -558,349 +560,6 @@ __global__ void __launch_bounds__(NT, MINB)
   DFA_STAMP(7);
 }
 
-// ------------------------------------------------------------------------------------------
-// forward with row merging and a balanced gather (the default for SimPB's shapes)
-// ------------------------------------------------------------------------------------------
-// What bounds the gather on B200 is not HBM but the SM's load path — every 128 bytes a warp pulls
-// into registers is one L1 wavefront, hit or miss (ncu: l1tex data pipe 71 % busy on the
-// row-sliced kernel while DRAM sits at 34 %) — and, at one batch item, the length of each warp's
-// dependent chain.  So this kernel pulls fewer rows and keeps every warp's loads independent.
-// The key points of one anchor project close together: at the coarse levels their bilinear
-// corners name the same feature rows again and again (camera-rig inputs: 230 corner references
-// per anchor, 106 distinct rows).  They are merged without sorting or atomics:
-//
-//   prologue (warp 0)  the anchor's sampling locations arrive by one TMA bulk copy; the warp
-//                      compacts the samples that pass the op's (0,1) test and issues the weights
-//                      as TMA bulk copies too — one 128-byte line per VALID sample when the anchor
-//                      is sparse (a sample's L*G weights are contiguous), the whole block when it
-//                      is dense or when the grid is so small that latency, not bandwidth, rules.
-//   merge              warp l owns level l.  A chunk = up to 8 valid samples = 32 corner references,
-//                      one per lane.  __match_any_sync groups lanes that name the same row; the
-//                      lowest lane of each group sums the group's (bilinear weight x group weight)
-//                      coefficients with shuffles in ascending lane order.  Across the chunks of
-//                      the level a small direct-mapped table (row -> slot) in shared memory lets a
-//                      leader find a row an earlier chunk already listed and add to its
-//                      coefficients instead.  Result: a list of (row offset, coef[G]) per warp.
-//   gather             after one barrier every warp takes the same share of every list (slot p of
-//                      list c goes to warp (p + c) mod NW), so the warps finish together.  A lane
-//                      owns VPL 16-byte vectors of a row: one warp instruction covers 512 contiguous
-//                      bytes, U rows are in flight per lane, and the weighted sum stays in
-//                      registers (packed FFMA2).
-//   epilogue           the warps' partial rows are folded through shared memory and the anchor's
-//                      output row is written once.
-//
-// Merge and summation order are fixed, so results are bitwise reproducible.
-
-// NW: warps per CTA.  U: rows in flight per lane.
-template <typename T, int VPL, int G, int NW, int U, bool TMA, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB)
-    dfa_fwd_merge_kernel(const T *__restrict__ feat, const int *__restrict__ shape,
-                         const int *__restrict__ start, const float *__restrict__ loc,
-                         const float *__restrict__ weights, float *__restrict__ out, Dims d,
-                         MergeLayout lay, int whole_weights) {
-  constexpr int VEC = FeatVec<T>::VEC;
-  constexpr int NT = NW * 32;
-  constexpr int GPV = G / VPL;  // groups covered by one 512-byte segment of the row
-  constexpr int C = 32 * VPL * VEC;
-  static_assert(G % 4 == 0 && G % VPL == 0 && (32 * VPL) % G == 0,
-                "a 16-byte vector must lie inside one group");
-  static_assert((NW & (NW - 1)) == 0 && NW >= 2 && NW <= 32, "warps per CTA: a power of two");
-  static_assert(MERGE_CAP * G >= C, "partial rows must fit the coefficient lists");
-  static_assert(U == 2 || U == 4, "row offsets / slots of a batch are read with one vector load");
-  extern __shared__ __align__(128) unsigned char smem[];
-  float *s_w = reinterpret_cast<float *>(smem + lay.w);
-  float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
-  uint32_t *s_list = reinterpret_cast<uint32_t *>(smem + lay.list);
-  int4 *s_tab = reinterpret_cast<int4 *>(smem + lay.tab);
-  uint32_t *s_rowoff = reinterpret_cast<uint32_t *>(smem + lay.rowoff);
-  float *s_coef = reinterpret_cast<float *>(smem + lay.coef);
-  int *s_cnt = reinterpret_cast<int *>(smem + lay.cnt);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + lay.bar);
-  int *s_nvalid = reinterpret_cast<int *>(bars + 2);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int anchor = blockIdx.x;  // b * A + a
-  const int b = anchor / d.A;
-  const int PK = d.P * d.K, LG = d.L * G, wcount = PK * LG;
-  const float *loc_g = loc + static_cast<size_t>(anchor) * PK * 2;
-  const float *w_g = weights + static_cast<size_t>(anchor) * wcount;
-  const unsigned lt_mask = (1u << lane) - 1u;
-
-  // ---- prologue ------------------------------------------------------------------------------
-  DFA_STAMP(0);
-  if (TMA) {
-    if (warp == 0) {
-      if (lane == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_mbar_init();
-        mbar_expect_tx(&bars[0], 8u * PK);
-        tma_bulk_g2s(s_loc, loc_g, 8u * PK, &bars[0]);
-        if (whole_weights) {
-          mbar_expect_tx(&bars[1], 4u * wcount);
-          tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
-        }
-      }
-      __syncwarp();
-      if (NW == 1)
-        for (int i = lane; i < d.K * d.L; i += 32)
-          s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
-      mbar_wait(&bars[0], 0);
-    } else {
-      for (int i = tid - 32; i < d.K * d.L; i += NT - 32)
-        s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
-    }
-  } else {
-    for (int i = tid; i < 2 * PK; i += NT) s_loc[i] = __ldg(loc_g + i);
-    for (int i = tid; i < d.K * d.L; i += NT)
-      s_tab[i] = make_int4(__ldg(shape + 2 * i), __ldg(shape + 2 * i + 1), __ldg(start + i), 0);
-    __syncthreads();
-  }
-  DFA_STAMP(1);
-  bool sparse_w = false;  // weight lines packed by valid-sample index (stride LG + MERGE_WPAD)
-  if (warp == 0) {
-    // compaction: entry = sample | camera << 16, in sample order
-    const float rK = 1.0f / static_cast<float>(d.K);
-    int n = 0;
-    for (int base = 0; base < PK; base += 32) {
-      const int s = base + lane;
-      bool v = false;
-      if (s < PK) {
-        const float2 xy = *reinterpret_cast<const float2 *>(s_loc + 2 * s);
-        v = sample_valid(xy.x, xy.y);
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, v);
-      if (v) {
-        const int p = static_cast<int>((static_cast<float>(s) + 0.5f) * rK);  // exact: s < 65536
-        s_list[n + __popc(m & lt_mask)] = static_cast<uint32_t>(s) | (static_cast<uint32_t>(s - p * d.K) << 16);
-      }
-      n += __popc(m);
-    }
-    sparse_w = TMA && !whole_weights && 2 * n <= PK;
-    if (lane == 0) *s_nvalid = sparse_w ? -n - 1 : n;
-    if (TMA && !whole_weights && n > 0) {
-      if (!sparse_w) {  // dense anchor: one copy of the whole block
-        if (lane == 0) {
-          mbar_expect_tx(&bars[1], 4u * wcount);
-          tma_bulk_g2s(s_w, w_g, 4u * wcount, &bars[1]);
-        }
-      } else {  // sparse anchor: one line per valid sample, packed by valid index
-        if (lane == 0) mbar_expect_tx(&bars[1], 4u * LG * n);
-        __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-          const int s = s_list[i] & 0xffff;
-          tma_bulk_g2s(s_w + i * (LG + MERGE_WPAD), w_g + s * LG, 4u * LG, &bars[1]);
-        }
-      }
-    }
-  }
-  DFA_STAMP(2);
-  __syncthreads();
-  DFA_STAMP(3);
-  int nv = *s_nvalid;
-  sparse_w = nv < 0;
-  nv = sparse_w ? -nv - 1 : nv;
-  if (!TMA) {  // plain staging of the valid samples' weight lines
-    for (int i = tid; i < nv * LG; i += NT) {
-      const int s = s_list[i / LG] & 0xffff, r = i - (i / LG) * LG;
-      s_w[s * LG + r] = __ldg(w_g + s * LG + r);
-    }
-    __syncthreads();
-  }
-  const int wstride = sparse_w ? LG + MERGE_WPAD : LG;
-
-  const uint32_t rb = 512u * VPL;  // bytes per feature row
-  const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
-                            static_cast<size_t>(b) * d.num_feat * rb + lane * 16;
-  const int gq = (lane * G) / (32 * VPL);  // this lane's group inside each 512-byte segment
-  float acc[VPL][VEC];
-#pragma unroll
-  for (int v = 0; v < VPL; ++v)
-#pragma unroll
-    for (int c = 0; c < VEC; ++c) acc[v][c] = 0.f;
-
-  // A warp's work items: (level, chunk of 8 valid samples) for its levels l = warp, warp + NW, ...
-  const int cpl = (nv + 7) >> 3;  // chunks per level
-  const int my_levels = warp < d.L ? (d.L - warp + NW - 1) / NW : 0;
-  const int max_items = ((d.L + NW - 1) / NW) * cpl;  // warp 0 has the most
-  uint32_t *s_table = reinterpret_cast<uint32_t *>(smem + lay.table) + warp * MERGE_TABLE;
-  uint32_t *my_rowoff = s_rowoff + warp * MERGE_CAP;
-  float *my_coef = s_coef + warp * MERGE_CAP * G;
-  uint32_t *s_mine_off = reinterpret_cast<uint32_t *>(smem + lay.mine_off) + warp * lay.mine_stride;
-  uint16_t *s_mine_slot = reinterpret_cast<uint16_t *>(smem + lay.mine_slot) + warp * lay.mine_stride;
-  bool wready = !TMA;
-  int li = 0, cj = 0;  // this warp's next item: its li-th level, chunk cj
-
-  for (int it0 = 0; it0 < max_items; it0 += 2) {
-    // ---- merge: this warp's next two chunks -------------------------------------------------------
-    int cnt = 0;
-    if (li < my_levels) {
-#pragma unroll
-      for (int x = 0; x < MERGE_TABLE / 128; ++x)
-        reinterpret_cast<uint4 *>(s_table)[x * 32 + lane] =
-            make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-      __syncwarp();
-    }
-    for (int x = 0; x < 2 && li < my_levels; ++x) {
-      const int l = warp + li * NW;
-      const int i = (cj << 3) + (lane >> 2), q = lane & 3;
-      if (++cj == cpl) cj = 0, ++li;
-      const bool live = i < nv;
-      const int ii = live ? i : 0;
-      const uint32_t ent = s_list[ii];
-      const int s = ent & 0xffff, k = ent >> 16;
-      const int4 tab = s_tab[k * d.L + l];
-      const float2 xy = *reinterpret_cast<const float2 *>(s_loc + 2 * s);
-      TapGeom gm;
-      tap_geometry(xy.x, xy.y, tab.x, tab.y, tab.z, gm);
-      const int row = q == 0 ? gm.row[0] : q == 1 ? gm.row[1] : q == 2 ? gm.row[2] : gm.row[3];
-      const float bw = ((q & 2) ? gm.lh : gm.hh) * ((q & 1) ? gm.lw : gm.hw);
-      const bool use = live && row >= 0;
-      const unsigned key = use ? static_cast<unsigned>(row) : (0x80000000u | lane);
-      const unsigned grp = __match_any_sync(0xffffffffu, key);
-      const bool leader = use && (static_cast<int>(__ffs(grp)) - 1 == lane);
-      if (!wready) {
-        mbar_wait(&bars[1], 0);  // weights have landed
-        wready = true;
-      }
-      // coefficients in the permuted order the gather reads them: [gq][v]  (g = v * GPV + gq)
-      float cf[G];
-      {
-        const float4 *wp = reinterpret_cast<const float4 *>(s_w + (sparse_w ? ii : s) * wstride + l * G);
-        float wv[G];
-#pragma unroll
-        for (int x = 0; x < G / 4; ++x) {
-          const float4 t = wp[x];
-          wv[4 * x] = t.x, wv[4 * x + 1] = t.y, wv[4 * x + 2] = t.z, wv[4 * x + 3] = t.w;
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) cf[(g % GPV) * VPL + g / GPV] = use ? bw * wv[g] : 0.f;
-      }
-      // leaders add the coefficients of the other lanes of their group, lowest lane first
-      unsigned rem = leader ? (grp & ~(1u << lane)) : 0u;
-      const int n_it = __reduce_max_sync(0xffffffffu, __popc(rem));
-      for (int it = 0; it < n_it; ++it) {
-        const int src = rem ? (static_cast<int>(__ffs(rem)) - 1) : lane;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float v = __shfl_sync(0xffffffffu, cf[g], src);
-          if (rem) cf[g] += v;
-        }
-        rem &= rem - 1;
-      }
-      // has an earlier chunk of this round listed the row already?
-      const uint32_t h = (static_cast<uint32_t>(row) * 0x9E3779B1u) >> 25;  // MERGE_TABLE = 128
-      const uint32_t e = leader ? s_table[h] : 0xffffffffu;
-      const bool hit = leader && (e >> 6) == static_cast<uint32_t>(row);
-      const bool fresh = leader && !hit;
-      const unsigned fresh_m = __ballot_sync(0xffffffffu, fresh);
-      const int slot = hit ? static_cast<int>(e & 63u) : cnt + __popc(fresh_m & lt_mask);
-      float4 *cp = reinterpret_cast<float4 *>(my_coef + slot * G);
-      if (hit) {
-#pragma unroll
-        for (int x = 0; x < G / 4; ++x) {
-          float4 t = cp[x];
-          t.x += cf[4 * x], t.y += cf[4 * x + 1], t.z += cf[4 * x + 2], t.w += cf[4 * x + 3];
-          cp[x] = t;
-        }
-      } else if (fresh) {
-        s_table[h] = (static_cast<uint32_t>(row) << 6) | static_cast<uint32_t>(slot);
-        my_rowoff[slot] = static_cast<uint32_t>(row) * rb;
-#pragma unroll
-        for (int x = 0; x < G / 4; ++x)
-          cp[x] = make_float4(cf[4 * x], cf[4 * x + 1], cf[4 * x + 2], cf[4 * x + 3]);
-      }
-      cnt += __popc(fresh_m);
-      __syncwarp();
-    }
-    if (lane == 0) s_cnt[warp] = cnt;
-    DFA_STAMP(4);
-    __syncthreads();
-    DFA_STAMP(5);
-    // ---- this warp's share: slot p of list c goes to warp (p + c) mod NW --------------------------
-    int n_mine = 0;
-#pragma unroll
-    for (int c = 0; c < NW; ++c) {
-      const int cn = s_cnt[c];
-      const int first = (warp - c) & (NW - 1);
-      const int mine = cn > first ? (cn - first + NW - 1) / NW : 0;
-      if (lane < mine) {
-        const int slot = c * MERGE_CAP + first + lane * NW;
-        s_mine_off[n_mine + lane] = s_rowoff[slot];
-        s_mine_slot[n_mine + lane] = static_cast<uint16_t>(slot);
-      }
-      n_mine += mine;
-    }
-    if (lane < U) {  // padding up to a multiple of U: no load, zero coefficients
-      s_mine_off[n_mine + lane] = 0xffffffffu;
-      s_mine_slot[n_mine + lane] = 0;
-    }
-    __syncwarp();
-    // ---- gather: every distinct row once ----------------------------------------------------------
-    for (int k0 = 0; k0 < n_mine; k0 += U) {
-      typename FeatVec<T>::raw_t val[U][VPL];
-      uint32_t off[U];
-      int slot[U];
-      if constexpr (U == 4) {
-        const uint4 o4 = *reinterpret_cast<const uint4 *>(s_mine_off + k0);
-        const uint2 s2 = *reinterpret_cast<const uint2 *>(s_mine_slot + k0);
-        off[0] = o4.x, off[1] = o4.y, off[2] = o4.z, off[3] = o4.w;
-        slot[0] = s2.x & 0xffff, slot[1] = s2.x >> 16, slot[2] = s2.y & 0xffff, slot[3] = s2.y >> 16;
-      } else {
-        const uint2 o2 = *reinterpret_cast<const uint2 *>(s_mine_off + k0);
-        const uint32_t s1 = *reinterpret_cast<const uint32_t *>(s_mine_slot + k0);
-        off[0] = o2.x, off[1] = o2.y;
-        slot[0] = s1 & 0xffff, slot[1] = s1 >> 16;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = off[u] != 0xffffffffu;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-          val[u][v] = ok ? FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + (off[u] + 512u * v)))
-                         : FeatVec<T>::zero_raw();
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = off[u] != 0xffffffffu;
-        const float *cp = s_coef + slot[u] * G + gq * VPL;
-        float cv[VPL];
-        if (VPL == 2) {
-          const float2 t = *reinterpret_cast<const float2 *>(cp);
-          cv[0] = ok ? t.x : 0.f, cv[VPL - 1] = ok ? t.y : 0.f;
-        } else {
-          cv[0] = ok ? *cp : 0.f;
-        }
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) FeatVec<T>::fma(acc[v], cv[v], val[u][v]);
-      }
-    }
-    DFA_STAMP(6);
-    __syncthreads();  // the lists are free again (next round, or the partial rows)
-  }
-  if (TMA && whole_weights && !wready) mbar_wait(&bars[1], 0);  // never exit with a copy in flight
-
-  // ---- epilogue: fold the warps' partial rows ---------------------------------------------------
-  {
-    float *part = s_coef + warp * C;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      float4 *o = reinterpret_cast<float4 *>(part + (v * 32 + lane) * VEC);
-#pragma unroll
-      for (int c = 0; c < VEC / 4; ++c)
-        o[c] = make_float4(acc[v][4 * c], acc[v][4 * c + 1], acc[v][4 * c + 2], acc[v][4 * c + 3]);
-    }
-  }
-  __syncthreads();
-  for (int c = tid; c < C; c += NT) {
-    float sum = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) sum += s_coef[w * C + c];
-    out[static_cast<size_t>(anchor) * C + c] = sum;
-  }
-  DFA_STAMP(7);
-}
-
 // Shape-generic forward (any C, G with C % G == 0, any alignment): one CTA per anchor, threads
 // stride over channels, scalar loads.  Same staging/geometry code, no atomics.
 template <typename T>
@@ -979,7 +638,6 @@ __global__ void dfa_debug_indices_kernel(const int *__restrict__ shape, const in
 
 }  // namespace
 
-#include "dfa_forward_pool.cuh"
 #include "dfa_forward_win.cuh"
 
 namespace {
@@ -1021,7 +679,7 @@ void last_wave_split(const Dims &d, int vpr, int ctas_per_sm, long long &split_f
   constexpr int VEC = FeatVec<T>::VEC;
   const long long total = static_cast<long long>(d.bs) * d.A;
   split_from = total, grid = total, split_log2 = 0;
-  const int mode = env_int("DFA_FWD_SPLIT", 1);
+  const int mode = DFA_KNOB("DFA_FWD_SPLIT", 1);
   const int max_log2 = ((d.C / 4) % VEC == 0 && vpr >= 4) ? 2 : (((d.C / 2) % VEC == 0 && vpr >= 2) ? 1 : 0);
   if (mode == 1 && max_log2 == 2) {
     static std::atomic<int> sm_count[64];  // 0 = not queried yet; racing threads store the same value
@@ -1032,7 +690,7 @@ void last_wave_split(const Dims &d, int vpr, int ctas_per_sm, long long &split_f
         sm_count[dev].store(sms, std::memory_order_relaxed);
       const long long slots = static_cast<long long>(sms) * ctas_per_sm;
       const long long rem = slots > 0 ? total % slots : 0;  // anchors of the last, partial wave
-      const int frac = env_int("DFA_FWD_SPLIT_FRAC", 2);  // split when the last wave is at most 1/frac full
+      const int frac = DFA_KNOB("DFA_FWD_SPLIT_FRAC", 2);  // split when the last wave is at most 1/frac full
       if (total > slots && rem > 0 && frac > 0 && rem <= slots / frac)
         split_from = total - rem, split_log2 = 2, grid = split_from + 4 * rem;
     }
@@ -1074,21 +732,6 @@ int rows_vpr(const Dims &d, const void *feat, int nt) {
   return vpr;
 }
 
-template <typename T, int VPL, int NW, int U, bool TMA, int MINB>
-int launch_fwd_merge(const void *feat, const int *shape, const int *start, const float *loc,
-                     const float *w, float *out, const Dims &d, cudaStream_t st) {
-  auto kern = dfa_fwd_merge_kernel<T, VPL, 8, NW, U, TMA, MINB>;
-  const MergeLayout lay = merge_layout(d.P, d.K, d.L, d.G, NW, U);
-  if (int rc = set_smem(kern, lay.total)) return rc;
-  // A grid that fits the machine in about one wave is bound by latency, not bandwidth: fetch the
-  // whole weights block at once instead of waiting for the sample mask first.
-  const long long grid = static_cast<long long>(d.bs) * d.A;
-  const int whole = env_int("DFA_FWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0);
-  kern<<<d.bs * d.A, NW * 32, lay.total, st>>>(static_cast<const T *>(feat), shape, start, loc, w,
-                                              out, d, lay, whole);
-  return static_cast<int>(cudaGetLastError());
-}
-
 template <typename T, int VPL, bool TMA, int NW, int MINB>
 int launch_fwd_win(const void *feat, const int *shape, const int *start, const float *loc,
                    const float *w, float *out, const Dims &d, cudaStream_t st) {
@@ -1096,8 +739,8 @@ int launch_fwd_win(const void *feat, const int *shape, const int *start, const f
   // A grid of about one wave is bound by latency: fetch the whole weights block with the locations
   // instead of the valid samples' weights next to the row loads.
   const long long grid = static_cast<long long>(d.bs) * d.A;
-  const int whole = TMA ? env_int("DFA_FWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0) : 0;
-  const int merge_pix = env_int("DFA_FWD_MERGE_PIX", WIN_MAP);
+  const int whole = TMA ? DFA_KNOB("DFA_FWD_WHOLE_WEIGHTS", grid <= 148 * 8 ? 1 : 0) : 0;
+  const int merge_pix = DFA_KNOB("DFA_FWD_MERGE_PIX", WIN_MAP);
   const WinLayout lay = win_layout(d.P, d.K, d.L, d.G, d.C, NW, whole != 0);
   if (int rc = set_smem(kern, lay.total)) return rc;
   // Channel split of the anchors that start last (see the kernel): DFA_FWD_TAIL_SPLIT = how many
@@ -1105,7 +748,7 @@ int launch_fwd_win(const void *feat, const int *shape, const int *start, const f
   long long split_from = grid;
   if (VPL == 2) {
     const long long slots = 148ll * MINB;
-    const long long n = slots * env_int("DFA_FWD_TAIL_SPLIT", 10) / 10 / 2;  // anchors -> two CTAs each
+    const long long n = slots * DFA_KNOB("DFA_FWD_TAIL_SPLIT", 10) / 10 / 2;  // anchors -> two CTAs each
     if (grid > 2 * slots && n > 0) split_from = grid - n;
   }
   kern<<<static_cast<unsigned int>(split_from + 2 * (grid - split_from)), NW * 32, lay.total, st>>>(
@@ -1117,35 +760,26 @@ template <typename T>
 int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
                   const float *w, float *out, const Dims &d, cudaStream_t st) {
   // DFA_FWD_VARIANT (tuning knob): 1..4 = row-sliced kernel with (threads, taps in flight) =
-  // (256,1) (256,2) (512,1) (512,2) — 1 is the default, the fastest measured on B200 at SimPB's
-  // shapes (192- and 128-thread CTAs and a 32-register build were tried and lost 20-40 %);
-  // 10..12 = row-merging kernel (fewer DRAM bytes and L1 wavefronts, longer dependent chain per
-  // warp: within 5-25 % of the default); 0 = one-warp-per-group kernel.
-  // A variant whose shape constraints are not met falls through to the next family.
-  // Default (no override): the row-sliced kernel with one tap in flight per thread, for fp32 and
-  // bfloat16 tables alike (with the channel split of the last wave it also beats the earlier
-  // bfloat16 picks: 14.1 vs 15.3 us (variant 2) at bs=1, 71.9 vs 72.9 us (variant 11) at bs=8).
-  // With many potential taps per anchor (more key points than SimPB's 13: P*K*L >= 400) the chains
-  // of dependent load rounds are long enough that two taps in flight at 4 CTAs per SM win: 26.7 vs
-  // 32.0 us at 20 key points, 38.2 vs 42.2 us at 32 (900 anchors, fp32; bf16 and 1800 / 3600 anchors
-  // alike, 5-17 %); at 13 key points it is the other way round (17.9 vs 21.5 us).
+  // (256,1) (256,2) (512,1) (512,2); 30..33 = warp-autonomous window-merging kernel with (warps,
+  // CTAs per SM) = (4,8) (8,4) (4,7) (2,16); 0 = one-warp-per-group kernel.  A variant whose shape
+  // constraints are not met falls through to the next family.
+  // Defaults, each the fastest measured on B200 (tools/sweep_fwd.py, tools/op_sweep.py, profiles/):
+  //  * the row-sliced kernel with one tap in flight per thread, fp32 and bfloat16 tables alike;
+  //  * with many potential taps per anchor (more key points than SimPB's 13: P*K*L >= 400) the chains
+  //    of dependent load rounds are long enough that two taps in flight at 4 CTAs per SM win (26.7
+  //    vs 32.0 us at 20 key points, 38.2 vs 42.2 us at 32; 900 anchors, fp32);
+  //  * many waves of anchors on a table that mostly lives in L2 (fp32 rows of 1 KB, at least 7,000
+  //    anchors, at most 128 MB per batch item — the training shapes): the window-merging kernel with
+  //    two warps per anchor.  There the path is bound by the L2 -> SM fabric, and merging the coarse
+  //    levels' taps moves 23 % fewer bytes over it: 88.0 vs 94.7 us at bs=8 x 900 anchors, 111.8 vs
+  //    120.8 us at 8 x 1,220.  On small grids its longer per-anchor chain loses (bs=1: 24 vs 18 us),
+  //    and R101 maps (368 MB per item, DRAM-bound) are par: both stay on the row-sliced kernel.
   const bool long_chains = static_cast<long long>(d.P) * d.K * d.L >= 400;
-  const int variant = env_int("DFA_FWD_VARIANT", long_chains ? 2 : 1);
-  if (variant >= 20 && variant < 30) {  // SM-pooled kernel: 20 = one 1024-thread CTA per SM, 21 = two 512-thread CTAs
-    const int vpl = pool_vpl<T>(d, feat, loc, out);
-    if (vpl) {
-      int rc;
-#define POOL(NT) (vpl == 2 ? launch_fwd_pool<T, 2, 1, NT>(feat, shape, start, loc, w, out, d, st)   \
-                           : launch_fwd_pool<T, 1, 2, NT>(feat, shape, start, loc, w, out, d, st))
-      if (variant == 21) rc = POOL(512);
-      else if (variant == 22)   // 768 threads: 85 registers, twice the taps in flight per lane
-        rc = vpl == 2 ? launch_fwd_pool<T, 2, 2, 768>(feat, shape, start, loc, w, out, d, st)
-                      : launch_fwd_pool<T, 1, 4, 768>(feat, shape, start, loc, w, out, d, st);
-      else rc = POOL(1024);
-#undef POOL
-      if (rc >= 0) return rc;
-    }
-  }
+  int dflt = long_chains ? 2 : 1;
+  if (!long_chains && sizeof(T) == 4 && static_cast<long long>(d.bs) * d.A >= 7000 &&
+      static_cast<long long>(d.num_feat) * d.C * 4 <= (128ll << 20) && win_vpl<T>(d, feat) == 2)
+    dflt = 33;
+  const int variant = DFA_KNOB("DFA_FWD_VARIANT", dflt);
   if (variant >= 30 && variant < 40) {  // warp-autonomous window-merging kernel
     const int vpl = win_vpl<T>(d, feat);
     if (vpl) {
@@ -1164,7 +798,7 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
 #undef WIN
     }
   }
-  const int rvariant = variant >= 10 ? 1 : variant;
+  const int rvariant = variant >= 5 ? 1 : variant;
   if (rvariant >= 1) {
     const int nt = rvariant >= 3 ? 512 : 256;
     const int vpr = rows_vpr<T>(d, feat, nt);
@@ -1208,6 +842,8 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
 extern "C" {
 
 int dfa_version(void) { return DFA_B200_VERSION; }
+
+void dfa_debug_reload_knobs(void) { dfa_knob_generation.fetch_add(1, std::memory_order_relaxed); }
 
 #ifdef DFA_PHASE_TIMING
 int dfa_debug_set_phase_buffer(long long *buf) {

@@ -32,3 +32,26 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _live_tuning_knobs(monkeypatch):
+    """libdfa_b200.so reads its DFA_* tuning environment variables once per process; tests that switch
+    kernels with monkeypatch.setenv need the library to look again (dfa_debug_reload_knobs)."""
+    if not _has_cuda():
+        yield
+        return
+    from simpb_b200 import cabi
+    cabi.reload_knobs()      # whatever the previous test left behind is gone
+    set_env, del_env = monkeypatch.setenv, monkeypatch.delenv
+
+    def setenv(name, value, *a, **k):
+        set_env(name, value, *a, **k)
+        cabi.reload_knobs()
+
+    def delenv(name, *a, **k):
+        del_env(name, *a, **k)
+        cabi.reload_knobs()
+
+    monkeypatch.setenv, monkeypatch.delenv = setenv, delenv
+    yield

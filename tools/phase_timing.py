@@ -58,7 +58,10 @@ torch.cuda.synchronize()
 t = buf.cpu().double()
 t = t[t[:, 0, 0] > 0]       # CTAs that ran
 rows_like = a.variant < 10 or a.variant >= 30
-if a.variant >= 30:    # window-merging kernel
+if a.variant >= 40:    # channel-sliced kernel
+    names = ["0 start", "1 locations landed, camera masks", "2 barrier + plan (+ weights landed)", "3 fine rows built, barrier",
+             "4 gather done", "5 end", "-", "-"]
+elif a.variant >= 30:    # window-merging kernel
     names = ["0 start", "1 locations landed, camera masks", "2 barrier (+ weights landed)", "3 fine-level taps done",
              "4 coarse-level units done", "5 end", "-", "-"]
 elif a.variant < 10:     # row-sliced kernel: its own stamp meanings

@@ -21,6 +21,7 @@ for inputs, batch, dt in cases:
     ref = None
     for v, pf in [(v, 0) for v in variants]:
         os.environ["DFA_FWD_VARIANT"] = str(v)
+        cabi.reload_knobs()
         fns = [(lambda g=g, o=o: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o))
                for g, o in zip(sets, outs)]
         ms = bench.time_graph(fns, 200, 20, True, torch.cuda.synchronize) / 200
