@@ -2,22 +2,31 @@
 """Benchmark of the deformable-feature-aggregation hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload fwd|train] [--batch B] [--inputs rig|uniform] [--dtype f32|bf16]
+                    [--workload fwd|train] [--batch B] [--anchors A] [--inputs rig|uniform]
+                    [--dtype f32|bf16] [--reps R] [--no-extras]
 
 One "step" = one pass of the op over one batch of synthetic SimPB-shaped input
 (R50 704x256: 6 cameras x 4 FPN levels = 89,760 feature rows x 256 channels; 900 anchors x 13
-key points x 8 groups).  Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how every
-number is defined.
+key points x 8 groups).  Prints ONE JSON line (rank 0).  See DESIGN.md §5 for how every number is
+defined.
 
 * value       queries/s = bs*A*N / step time, inputs resident in HBM but cold in L2 (the step
               rotates over input sets whose total size exceeds the 126 MB L2), CUDA events on the
-              launching stream, max over ranks.
+              launching stream.  The timed region of exactly K steps (barrier + synchronize on both
+              sides, max over ranks) is repeated `--reps` times and the MEDIAN region is reported, so a
+              20-launch region on 8 GPUs is not timer noise (`timing` holds min / median / max).
 * e2e         the same metric through the C ABI's host-buffer entry point (dfa_forward_host):
-              pinned host inputs → device, kernel, output → host, every step.
-* roofline    algorithmic bytes of SURVEY.md §8(d) / kernel time, against the measured HBM peak.
-* cpu_baseline the reference's grid_sample CPU path (port under oracle/), bounded sample.
+              pinned host inputs -> device, kernel, output -> host, every step; per-rank values and
+              achieved host-to-device GB/s beside it, plus the same with a bfloat16 table on the host.
+* roofline    algorithmic bytes of SURVEY.md §8(d) / kernel time, against the measured HBM peak; also
+              holds (keys the driver keeps) the bs=8 and R101 forward fractions, the unmodified
+              reference CUDA op's times on the same GPU, and the `train` record: forward + backward at 8
+              items per GPU x 1,220 anchors with the NCCL all-reduce of the DFA gradient bucket.
+* cpu_baseline the reference's grid_sample CPU path on the host cores, bounded sample: the reference's
+              own Python (staged under oracle/_ref/py by build()) when present, else the port.
 """
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -25,6 +34,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 import torch
 
@@ -34,6 +44,8 @@ sys.path.insert(0, ROOT)
 METRIC = "deformable_aggregation_forward_queries_per_sec"
 UNIT = "queries/s"
 L2_BYTES = 126e6
+TRAIN_ANCHORS = 1220          # 900 + up to 320 denoising anchors (models/simpb_head.py:371-379)
+BUCKET_FLOATS = 3 * 247495    # parameters of the three DFA layers of a frame
 
 
 def parse():
@@ -47,12 +59,28 @@ def parse():
     ap.add_argument("--anchors", type=int, default=900)
     ap.add_argument("--inputs", default="rig", choices=["rig", "uniform"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--reps", type=int, default=31, help="repetitions of the timed region (median reported)")
     ap.add_argument("--no-graph", action="store_true", help="launch step by step (no CUDA graph)")
-    ap.add_argument("--no-extras", action="store_true", help="skip variants / baselines")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary shapes / baselines")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------- helpers
+_SYN = None
+
+
+def synthetic():
+    """simpb_b200/synthetic.py loaded BY PATH: the input generator is plain torch, and importing the
+    package would dlopen libdfa_b200.so — which the reference arm must not do."""
+    global _SYN
+    if _SYN is None:
+        spec = importlib.util.spec_from_file_location("dfa_bench_synthetic",
+                                                      os.path.join(ROOT, "simpb_b200", "synthetic.py"))
+        _SYN = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_SYN)
+    return _SYN
+
+
 def measured_traffic(args):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, taken from the
     committed ncu capture of this exact workload (profiles/traffic.json); None if never captured."""
@@ -113,18 +141,21 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def make_inputs(args, seed, A=None, batch=None, levels=None):
-    from simpb_b200 import synthetic
-    maker = synthetic.rig_op_inputs if args.inputs == "rig" else synthetic.op_inputs_uniform
-    kw = dict(bs=batch or args.batch, A=A or args.anchors, seed=seed)
+def make_inputs(args, seed, A=None, batch=None, levels=None, feat=True):
+    syn = synthetic()
+    maker = syn.rig_op_inputs if args.inputs == "rig" else syn.op_inputs_uniform
+    kw = dict(bs=batch or args.batch, A=A or args.anchors, seed=seed, feat=feat)
     if levels is not None:
         kw["levels"] = levels
     return maker(**kw)
 
 
 def to_device(d, dtype):
-    return dict(feat=d["mc_ms_feat"].cuda().to(dtype).contiguous(),
-                shape=d["spatial_shape"].int().cuda(), start=d["scale_start_index"].int().cuda(),
+    if d["mc_ms_feat"] is None:   # secondary shapes: the table's values do not matter for the clock
+        feat = torch.randn(d["sampling_location"].shape[0], d["num_feat"], 256, device="cuda").to(dtype)
+    else:
+        feat = d["mc_ms_feat"].cuda().to(dtype).contiguous()
+    return dict(feat=feat, shape=d["spatial_shape"].int().cuda(), start=d["scale_start_index"].int().cuda(),
                 loc=d["sampling_location"].cuda().contiguous(), w=d["weights"].cuda().contiguous(),
                 go=d["grad_output"].cuda().contiguous())
 
@@ -138,12 +169,24 @@ def algorithmic_bytes(d, esz, distinct_rows):
     return fixed + distinct_rows * C * esz, fixed + bs * d["num_feat"] * C * esz
 
 
-def time_graph(fn_list, steps, warmup, use_graph, sync_all, finalize=None):
-    """Times `steps` launches cycling through fn_list (one callable per rotating input set).
-    Returns total milliseconds measured by CUDA events on the current stream."""
+def backward_bytes(d, esz, U):
+    """backward = 2 x locations + 2 x weights + grad_out + the referenced rows once more
+    + the zero fill of grad_mc_ms_feat + the read-modify-write of the touched gradient rows."""
+    bs, A, P, K, _ = d["sampling_location"].shape
+    L, G = d["weights"].shape[4:6]
+    C = 256
+    return (2 * 8 * bs * A * P * K + 2 * 4 * bs * A * P * K * L * G + 4 * bs * A * C
+            + U * C * esz + bs * d["num_feat"] * C * 4 + 2 * U * C * 4)
+
+
+def time_regions(fn_list, steps, warmup, use_graph, sync_all, finalize=None, reps=1):
+    """Times `reps` regions of exactly `steps` launches cycling through fn_list (one callable per
+    rotating input set).  Returns the list of region times in milliseconds (CUDA events on the
+    launching stream; `sync_all` = barrier + synchronize on both sides of every region)."""
     n = len(fn_list)
     stream = torch.cuda.Stream()
     stream.wait_stream(torch.cuda.current_stream())
+    out = []
     with torch.cuda.stream(stream):
         for i in range(max(warmup, 3)):
             fn_list[i % n]()
@@ -161,42 +204,64 @@ def time_graph(fn_list, steps, warmup, use_graph, sync_all, finalize=None):
                     finalize()  # side streams forked inside the capture (all-reduce) join it here
             graph.replay()
             stream.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
-        e0.record(stream)
-        if graph is not None:
-            for _ in range(steps // n):
-                graph.replay()
-            for i in range(steps % n):
-                fn_list[i]()
-        else:
-            for i in range(steps):
-                fn_list[i % n]()
-        if finalize is not None:
-            finalize()          # e.g. join the communication stream: its work belongs to the steps
-        e1.record(stream)
-        stream.synchronize()
-        sync_all()
-    return e0.elapsed_time(e1)
+        for _ in range(max(reps, 1)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sync_all()
+            e0.record(stream)
+            if graph is not None:
+                for _ in range(steps // n):
+                    graph.replay()
+                for i in range(steps % n):
+                    fn_list[i]()
+            else:
+                for i in range(steps):
+                    fn_list[i % n]()
+            if finalize is not None:
+                finalize()          # e.g. join the communication stream: its work belongs to the steps
+            e1.record(stream)
+            stream.synchronize()
+            sync_all()
+            out.append(e0.elapsed_time(e1))
+    return out
+
+
+def time_graph(fn_list, steps, warmup, use_graph, sync_all, finalize=None):
+    """One region (tools/ use this): total milliseconds of `steps` launches."""
+    return time_regions(fn_list, steps, warmup, use_graph, sync_all, finalize, 1)[0]
 
 
 # ----------------------------------------------------------------------------- CPU baseline
 def cpu_reference_setup(args):
     """The reference's CPU path = grid_sample per level + weighted fusion
-    (/root/reference/projects/mmdet3d_plugin/models/blocks.py:148-156, :215-261), restated in
-    oracle/module_ref.py.  One batch item of the bench workload per call."""
-    from oracle import module_ref
+    (/root/reference/projects/mmdet3d_plugin/models/blocks.py:148-156, :215-261) on one batch item of
+    the bench workload.  With the reference's own files staged (oracle/_ref/py, or /root/reference in
+    the build container) the step calls the REFERENCE'S feature_sampling + multi_view_level_fusion
+    (kind "reference"); otherwise the restatement in oracle/module_ref.py (kind "port")."""
+    from oracle import module_ref, ref_import
     d = make_inputs(args, seed=0, batch=1)
     maps = module_ref.unflatten_feature_maps(d["mc_ms_feat"], d["spatial_shape"],
                                              d["scale_start_index"])
-    uv = d["sampling_location"].permute(0, 3, 1, 2, 4).contiguous()        # [bs,K,A,P,2]
     w = d["weights"].permute(0, 1, 3, 4, 2, 5).contiguous()                # [bs,A,K,L,P,G]
-    G = w.shape[-1]
+    A, P, G = w.shape[1], w.shape[4], w.shape[-1]
+    root = ref_import.default_root() if args.inputs == "rig" else None
+    if root is not None:
+        blocks, _ = ref_import.import_reference(root)
+        DFA = blocks.DeformableFeatureAggregation
+        me = types.SimpleNamespace(num_groups=G, group_dims=256 // G, num_pts=P, embed_dims=256)
+        kp, proj, wh = d["key_points"], d["projection_mat"], d["image_wh"]
+
+        def step():
+            with torch.no_grad():
+                f = DFA.feature_sampling(maps, kp, proj, wh)                # blocks.py:215-245
+                f = DFA.multi_view_level_fusion(me, f, w)                   # blocks.py:247-261
+                return f.sum(dim=2)                                         # blocks.py:156
+        return step, A, "reference"
+    uv = d["sampling_location"].permute(0, 3, 1, 2, 4).contiguous()        # [bs,K,A,P,2]
 
     def step():
         with torch.no_grad():
             return module_ref.aggregate_grid_sample(maps, uv, w, G, apply_op_mask=False)
-    return step, d["sampling_location"].shape[1]
+    return step, A, "port"
 
 
 def time_cpu(step, steps, warmup):
@@ -215,38 +280,68 @@ def run_reference_arm(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count())
-    step, A = cpu_reference_setup(args)
+    step, A, kind = cpu_reference_setup(args)
     ts = time_cpu(step, args.steps, max(args.warmup, 1))
     ms = 1e3 * sum(ts) / len(ts)
     val = A / (ms / 1e3)
-    sample = "1 batch item (%d anchors) of the %s workload per step, all host threads" % (A, args.inputs)
+    sample = ("op level (grid_sample x 4 levels + weighted fusion for given key points and weights; no "
+              "weights_fc / key-point FCs): 1 batch item (%d anchors) of the %s workload per step, all host "
+              "threads; %s" % (A, args.inputs,
+                               "the reference's own feature_sampling + multi_view_level_fusion "
+                               "(models/blocks.py:215-261)" if kind == "reference"
+                               else "port of models/blocks.py:215-261 under oracle/"))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": workload_config(args, note="reference CPU path (grid_sample), port under oracle/"),
+            "data": "synthetic", "config": workload_config(args),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(),
-                             "kind": "port", "sample": sample},
+                             "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_config(args, note=None):
-    c = {"workload": "deformable_aggregation %s, SimPB R50 704x256 shape: %d batch item(s)/GPU x "
-                     "%d anchors x 13 key points x 6 cams x 4 levels x 8 groups, C=256"
-                     % ("forward" if args.workload == "fwd" else "forward+backward",
-                        args.batch, args.anchors),
-         "inputs": ("S1 camera-rig geometry (~19% of samples valid)" if args.inputs == "rig"
-                    else "S0 uniform locations in (-0.1,1.1) (~69% valid)"),
-         "feature_dtype": args.dtype, "batch_per_gpu": args.batch, "anchors": args.anchors,
-         "l2": "cold: steps rotate over input sets totalling more than the 126 MB L2"}
-    if note:
-        c["note"] = note
-    return c
+def workload_config(args):
+    return {"workload": "deformable_aggregation %s, SimPB R50 704x256 shape: %d batch item(s)/GPU x "
+                        "%d anchors x 13 key points x 6 cams x 4 levels x 8 groups, C=256"
+                        % ("forward" if args.workload == "fwd" else "forward+backward",
+                           args.batch, args.anchors),
+            "inputs": ("S1 camera-rig geometry (~19% of samples valid)" if args.inputs == "rig"
+                       else "S0 uniform locations in (-0.1,1.1) (~69% valid)"),
+            "feature_dtype": args.dtype, "batch_per_gpu": args.batch, "anchors": args.anchors,
+            "l2": "cold: steps rotate over input sets totalling more than the 126 MB L2"}
 
 
 # ----------------------------------------------------------------------------- own arm
+def train_step_fns(cabi, sets, outs, bucket):
+    """The training step of the op: forward, backward (grad_mc_ms_feat zero-filled by the library on the
+    stream, the two small gradients written in full), then — with a bucket — the data-parallel
+    all-reduce (mean) of a gradient bucket the size of the three DFA layers' parameters, enqueued on a
+    side stream so that it overlaps the next step's kernels."""
+    gfs = [torch.empty_like(g["feat"], dtype=torch.float32) for g in sets[:1]]
+    gls = [torch.empty_like(g["loc"]) for g in sets]
+    gws = [torch.empty_like(g["w"]) for g in sets]
+
+    def mk(i, g, o):
+        def f():
+            cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o)
+            cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
+                          gfs[0], gls[i], gws[i], flags=cabi.BWD_OVERWRITE_SMALL | cabi.BWD_ZERO_GRAD_FEAT)
+            if bucket is not None:
+                bucket.wait()                 # the previous step's all-reduce must have landed
+                bucket.all_reduce_mean()
+        return f
+    return [mk(i, g, o) for i, (g, o) in enumerate(zip(sets, outs))]
+
+
+def make_bucket(dist):
+    from simpb_b200 import parallel
+    params = [torch.nn.Parameter(torch.zeros(BUCKET_FLOATS // 3, device="cuda")) for _ in range(3)]
+    for p in params:
+        p.grad = torch.ones_like(p)
+    return parallel.GradBucket(params, comm_stream=torch.cuda.Stream()) if dist is not None else None
+
+
 def run_own_arm(args):
     from simpb_b200 import cabi
     rank = int(os.environ.get("RANK", "0"))
@@ -264,6 +359,20 @@ def run_own_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(values):
+        t = torch.tensor(values, device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def gather_ranks(value):
+        t = torch.tensor([value], device="cuda", dtype=torch.float64)
+        if dist is None:
+            return [float(value)]
+        ts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(ts, t)
+        return [float(x.item()) for x in ts]
+
     dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
     esz = 4 if args.dtype == "f32" else 2
     host = [make_inputs(args, seed=1000 * rank + s) for s in range(1)]
@@ -280,43 +389,11 @@ def run_own_arm(args):
         fns = [(lambda g=g, o=o: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o))
                for g, o in zip(sets, outs)]
     else:
-        # training step of the op: forward, backward (grad_feat memset inside), then the data-parallel
-        # all-reduce (mean) of a gradient bucket the size of the three DFA layers' parameters
-        # (3 x 247,495 fp32), enqueued on a side stream so it overlaps the next step's kernels
-        from simpb_b200 import parallel
-        gfs = [torch.empty_like(g["feat"], dtype=torch.float32) for g in sets[:2]]
-        gls = [torch.empty_like(g["loc"]) for g in sets]
-        gws = [torch.empty_like(g["w"]) for g in sets]
-        params = [torch.nn.Parameter(torch.zeros(247495, device="cuda")) for _ in range(3)]
-        for p in params:
-            p.grad = torch.ones_like(p)
-        bucket = None
-        if dist is not None:
-            bucket = parallel.GradBucket(params, comm_stream=torch.cuda.Stream())
+        bucket = make_bucket(dist)
+        if bucket is not None:
             finalize = bucket.wait
         launches_per_step = 3          # forward, grad_feat memset, backward (+ NCCL's own kernels)
-
-        fill_stream = torch.cuda.Stream()
-
-        def mk(i, g, o):
-            def f():
-                # what DeformableAggregationFunction does: the zero-fill of the scatter target runs
-                # on a side stream under the forward, the backward waits for it
-                cur = torch.cuda.current_stream()
-                fill_stream.wait_stream(cur)
-                with torch.cuda.stream(fill_stream):
-                    gfs[i % 2].zero_()
-                    filled = torch.cuda.Event()
-                    filled.record(fill_stream)
-                cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o)
-                cur.wait_event(filled)
-                cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
-                              gfs[i % 2], gls[i], gws[i], flags=cabi.BWD_OVERWRITE_SMALL)
-                if bucket is not None:
-                    bucket.wait()                 # previous step's all-reduce must have landed
-                    bucket.all_reduce_mean()
-            return f
-        fns = [mk(i, g, o) for i, (g, o) in enumerate(zip(sets, outs))]
+        fns = train_step_fns(cabi, sets, outs, bucket)
 
     # The NCCL all-reduce is captured into the CUDA graph with the kernels (one launch per replay
     # instead of ~20 eager launches per step); DFA_BENCH_EAGER_DIST=1 keeps the multi-GPU training
@@ -324,11 +401,9 @@ def run_own_arm(args):
     use_graph = not args.no_graph and not (args.workload == "train" and dist is not None
                                            and os.environ.get("DFA_BENCH_EAGER_DIST") == "1")
     with ClockSampler(local) as clk:
-        total_ms = time_graph(fns, args.steps, args.warmup, use_graph, sync_all, finalize)
-    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+        regions = max_over_ranks(time_regions(fns, args.steps, args.warmup, use_graph, sync_all, finalize,
+                                              args.reps))
+    total_ms = statistics.median(regions)
     ms_step = total_ms / args.steps
     queries = args.batch * args.anchors * world
     value = queries / (ms_step / 1e3)
@@ -342,7 +417,6 @@ def run_own_arm(args):
         ab = [algorithmic_bytes(d, esz, ui) for d, ui in zip(host, u)]
         b_alg = sum(a for a, _ in ab) / len(ab)
         b_full = sum(f for _, f in ab) / len(ab)
-        roof = None
         if args.workload == "fwd":
             ach = b_alg / (ms_step * 1e-3) / 1e9
             achf = b_full / (ms_step * 1e-3) / 1e9
@@ -354,18 +428,11 @@ def run_own_arm(args):
                     "peak_source": peak_src,
                     "whole_pyramid_variant": {"bytes": b_full, "achieved": achf, "frac": achf / peak}}
         else:
-            # forward + backward of the op: the forward's bytes, plus for the backward
-            # 2 x locations + 2 x weights + grad_out + the referenced rows once more + the zero fill of
-            # grad_mc_ms_feat + the read-modify-write of the touched gradient rows
-            d0 = host[0]
-            bs, A, P, K, _ = d0["sampling_location"].shape
-            L, G = d0["weights"].shape[4:6]
-            C, U = 256, sum(u) / len(u)
-            b_bwd = (2 * 8 * bs * A * P * K + 2 * 4 * bs * A * P * K * L * G + 4 * bs * A * C
-                     + U * C * esz + bs * d0["num_feat"] * C * 4 + 2 * U * C * 4)
+            U = sum(u) / len(u)
+            b_bwd = backward_bytes(host[0], esz, U)
             ach = (b_alg + b_bwd) / (ms_step * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "kernel": "dfa_fwd_rows_kernel + grad fill + dfa_bwd_merge_kernel",
+                    "traffic": None, "kernel": "forward + grad fill + dfa_bwd_merge_kernel",
                     "kernel_us": ms_step * 1e3, "algorithmic_bytes": b_alg + b_bwd,
                     "distinct_rows": U, "peak_source": peak_src,
                     "note": "whole training step of the op (all-reduce overlapped when n_gpus > 1)"}
@@ -374,51 +441,75 @@ def run_own_arm(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": workload_config(args), "clocks": clk.summary(),
-                "gpu_launches": launches_per_step * args.steps, "cuda_graph": bool(use_graph),
+                "gpu_launches": launches_per_step * args.steps * max(args.reps, 1), "cuda_graph": bool(use_graph),
+                "timing": {"regions": len(regions), "steps_per_region": args.steps,
+                           "region_ms_min": min(regions), "region_ms_median": total_ms,
+                           "region_ms_max": max(regions), "reported": "median region / steps, max over ranks"},
                 "roofline": roof}
 
-    # ---- end to end through the host-buffer C ABI entry point (every rank, max over ranks)
-    d0 = host[0]
-    dims = cabi.Dims(args.batch, 6, d0["num_feat"], 256, 4, args.anchors, 13, 8)
-    hf = cabi.HostForward(dims, dtype)
-    pin = lambda x: x.contiguous().pin_memory()  # noqa: E731
-    h = [dict(feat=pin(d["mc_ms_feat"].to(dtype)), shape=pin(d["spatial_shape"].int()),
-              start=pin(d["scale_start_index"].int()), loc=pin(d["sampling_location"]),
-              w=pin(d["weights"])) for d in host[:2]]
-    h_out = torch.empty(args.batch, args.anchors, 256).pin_memory()
-    e2e_steps = max(3, min(args.steps, 20))
-    for i in range(3):
-        hf(h[i % 2]["feat"], h[i % 2]["shape"], h[i % 2]["start"], h[i % 2]["loc"], h[i % 2]["w"], h_out)
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        x = h[i % 2]
-        hf(x["feat"], x["shape"], x["start"], x["loc"], x["w"], h_out)   # ends with a stream sync
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    if rank == 0:
-        x = h[0]
-        h2d = sum(x[k].numel() * x[k].element_size() for k in ("feat", "shape", "start", "loc", "w"))
-        line["e2e"] = {"value": queries / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
-                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h_out.numel() * 4,
-                       "api": "dfa_forward_host (C ABI, pinned host buffers)", "steps": e2e_steps}
+    # ---- end to end through the host-buffer C ABI entry point (every rank; the slowest rank counts)
+    def e2e_leg(dt):
+        d0 = host[0]
+        dims = cabi.Dims(args.batch, 6, d0["num_feat"], 256, 4, args.anchors, 13, 8)
+        hf = cabi.HostForward(dims, dt)
+        pin = lambda x: x.contiguous().pin_memory()  # noqa: E731
+        h = [dict(feat=pin(d["mc_ms_feat"].to(dt)), shape=pin(d["spatial_shape"].int()),
+                  start=pin(d["scale_start_index"].int()), loc=pin(d["sampling_location"]),
+                  w=pin(d["weights"])) for d in host[:2]]
+        h_out = torch.empty(args.batch, args.anchors, 256).pin_memory()
+        n = max(3, min(args.steps, 20))
+        for i in range(3):
+            hf(h[i % 2]["feat"], h[i % 2]["shape"], h[i % 2]["start"], h[i % 2]["loc"], h[i % 2]["w"], h_out)
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(n):
+            x = h[i % 2]
+            hf(x["feat"], x["shape"], x["start"], x["loc"], x["w"], h_out)   # ends with a stream sync
+        ms = 1e3 * (time.perf_counter() - t0) / n
+        h2d = sum(h[0][k].numel() * h[0][k].element_size() for k in ("feat", "shape", "start", "loc", "w"))
+        per_rank = gather_ranks(ms)
+        del hf, h
+        return {"ms_per_step": max(per_rank), "per_rank_ms": per_rank, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": h_out.numel() * 4, "steps": n,
+                "h2d_GBps_per_rank": [h2d / (m * 1e-3) / 1e9 for m in per_rank],
+                "h2d_GBps_all_ranks": sum(h2d / (m * 1e-3) / 1e9 for m in per_rank)}
 
-    # ---- baselines and variants (rank 0, N=1 only)
+    e = e2e_leg(dtype)
+    e_bf16 = e2e_leg(torch.bfloat16) if dtype != torch.bfloat16 else None
+    if rank == 0:
+        line["e2e"] = {"value": queries / (e["ms_per_step"] / 1e3), "unit": UNIT,
+                       "api": "dfa_forward_host (C ABI, pinned host buffers)", **e,
+                       "limiter": "the host link: one PCIe Gen5 x16 per GPU (~55 GB/s achieved); with several "
+                                  "ranks also the host's memory / root-complex bandwidth (h2d_GBps_all_ranks)",
+                       "cpu_affinity_cores": len(os.sched_getaffinity(0))}
+        if e_bf16 is not None:
+            line["e2e"]["bf16_table"] = {"value": queries / (e_bf16["ms_per_step"] / 1e3), "unit": UNIT, **e_bf16,
+                                         "note": "same call with a bfloat16 feature table on the host: "
+                                                 "half the bytes over the link"}
+
+    # ---- the training configuration on every rank (BASELINE.json config #3)
+    if not args.no_extras and args.workload == "fwd":
+        tr = train_record(args, cabi, dist, world, rank, sync_all, max_over_ranks)
+        if rank == 0:
+            line["roofline"]["train"] = tr
+
+    # ---- baselines and secondary shapes (rank 0, N=1 only)
     if rank == 0 and world == 1:
         torch.set_num_threads(os.cpu_count())
-        step, A = cpu_reference_setup(args)
+        step, A, kind = cpu_reference_setup(args)
         ts = time_cpu(step, 8, 1)
         cpu_ms = 1e3 * statistics.median(ts)
         line["cpu_baseline"] = {
             "value": A / (cpu_ms / 1e3), "unit": UNIT, "cores": torch.get_num_threads(),
-            "kind": "port", "ms_per_forward": cpu_ms,
-            "sample": "1 batch item (%d anchors), reference grid_sample path, median of 8 after 1 "
-                      "warm-up" % A}
+            "kind": kind, "ms_per_forward": cpu_ms,
+            "sample": "op level (grid_sample + fusion for given key points and weights): 1 batch item "
+                      "(%d anchors), median of 8 after 1 warm-up; %s" % (
+                          A, "the reference's own feature_sampling + multi_view_level_fusion"
+                          if kind == "reference" else "port under oracle/")}
         if not args.no_extras:
-            line["variants"] = extras(args, cabi, sets, host, peak)
+            del sets, outs
+            torch.cuda.empty_cache()
+            extras(args, cabi, host, peak, line["roofline"])
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
@@ -426,51 +517,136 @@ def run_own_arm(args):
         dist.destroy_process_group()
 
 
-def extras(args, cabi, sets, host, peak):
-    """Secondary measurements reported beside the headline (same timing method)."""
-    out = {}
+def train_record(args, cabi, dist, world, rank, sync_all, max_over_ranks):
+    """BASELINE.json config #3 on the driver's clock: forward + backward at 8 batch items per GPU x
+    1,220 anchors (900 + 320 denoising, models/simpb_head.py:371-379), followed by the NCCL
+    all-reduce (mean) of the 3 x 247,495-float DFA gradient bucket (apis/mmdet_train.py:97-102).
+    Reports the step with and without the collective (their difference is what data parallelism costs:
+    the weak-scaling loss) and the all-reduce alone."""
+    bs, A = 8, TRAIN_ANCHORS
+    a2 = argparse.Namespace(**vars(args))
+    a2.batch, a2.anchors, a2.workload = bs, A, "train"
+    host = [make_inputs(a2, seed=7000 + 100 * rank + s, feat=False) for s in range(2)]
+    sets = [to_device(d, torch.float32) for d in host]
+    outs = [torch.empty(bs, A, 256, device="cuda") for _ in sets]
+    steps, reps = 8, 9
+    local_fns = train_step_fns(cabi, sets, outs, None)
+    t_local = statistics.median(max_over_ranks(time_regions(local_fns, steps, 4, True, sync_all, None, reps)))
+    rec = {"workload": "forward + backward, %d items/GPU x %d anchors, fp32, rig inputs, cold L2" % (bs, A),
+           "n_gpus": world, "ms_per_step_no_allreduce": t_local / steps,
+           "timing": "median of %d regions of %d steps, max over ranks" % (reps, steps)}
+    if dist is not None:
+        bucket = make_bucket(dist)
+        fns = train_step_fns(cabi, sets, outs, bucket)
+        t = statistics.median(max_over_ranks(time_regions(fns, steps, 4, True, sync_all, bucket.wait, reps)))
+        rec["ms_per_step"] = t / steps
+
+        def ar():
+            bucket.all_reduce_mean()
+            bucket.wait()
+        t_ar = statistics.median(max_over_ranks(time_regions([ar], 20, 5, True, sync_all, None, reps)))
+        rec["allreduce_alone_us"] = t_ar / 20 * 1e3
+        rec["allreduce_bytes"] = 4 * BUCKET_FLOATS
+        rec["allreduce_cost_in_step_us"] = (t - t_local) / steps * 1e3
+        rec["weak_scaling_efficiency_vs_no_collective"] = t_local / t
+        rec["limiter"] = ("all-reduce latency: a 3 MB message is in NCCL's latency-bound regime; it runs on a "
+                          "side stream under the next step's forward, what is left shows in "
+                          "allreduce_cost_in_step_us")
+    else:
+        rec["ms_per_step"] = t_local / steps
+    rec["queries_per_s"] = bs * A * world / (rec["ms_per_step"] * 1e-3)
+    if rank == 0:
+        import oracle
+        U = oracle.distinct_rows(host[0]["spatial_shape"], host[0]["scale_start_index"],
+                                 host[0]["sampling_location"], host[0]["num_feat"])
+        b = algorithmic_bytes(host[0], 4, U)[0] + backward_bytes(host[0], 4, U)
+        rec["algorithmic_bytes_per_step_per_gpu"] = b
+        rec["frac_of_measured_hbm"] = b / (rec["ms_per_step"] * 1e-3) / 1e9 / peaks()[0]
+    del sets, outs
+    torch.cuda.empty_cache()
+    return rec
+
+
+def extras(args, cabi, host, peak, roof):
+    """Secondary measurements written INTO the roofline object (the driver keeps that key): the
+    forward at bs=8 and at R101 maps (BASELINE.json config #4), warm-L2 and backward times of the
+    headline shape, and the unmodified reference CUDA op on the same GPU and inputs."""
+    import oracle
     nosync = torch.cuda.synchronize
+    syn = synthetic()
 
-    def t_of(fns, steps=100):
-        return time_graph(fns, steps, 10, True, nosync) / steps
+    def fwd_point(levels, bs, A, n_sets=2, steps=40):
+        a2 = argparse.Namespace(**vars(args))
+        hs = [make_inputs(a2, seed=9000 + s, A=A, batch=bs, levels=levels, feat=False) for s in range(n_sets)]
+        ss = [to_device(d, torch.float32) for d in hs]
+        os_ = [torch.empty(bs, A, 256, device="cuda") for _ in ss]
+        fns = [(lambda g=g, o=o: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o))
+               for g, o in zip(ss, os_)]
+        ms = statistics.median(time_regions(fns, steps, 6, True, nosync, None, 7)) / steps
+        U = oracle.distinct_rows(hs[0]["spatial_shape"], hs[0]["scale_start_index"], hs[0]["sampling_location"],
+                                 hs[0]["num_feat"])
+        b_alg = algorithmic_bytes(hs[0], 4, U)[0]
+        rec = {"kernel_us": ms * 1e3, "algorithmic_bytes": b_alg, "achieved_GBps": b_alg / (ms * 1e-3) / 1e9,
+               "frac": b_alg / (ms * 1e-3) / 1e9 / peak, "queries_per_s": bs * A / (ms * 1e-3)}
+        return rec, ss
 
-    fwd = [(lambda g=g: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])) for g in sets]
+    other = {}
     try:
-        # warm L2: one input set over and over
-        ms = t_of(fwd[:1])
-        out["fwd_warm_l2_us"] = ms * 1e3
-        # backward (cold), grad_feat zero-fill included
+        other["r50_bs8"], ss8 = fwd_point(syn.R50_LEVELS, 8, 900)
+        # the unmodified reference CUDA op (oracle/_ref, built by oracle/build_ref.py) at bs=8
+        ref = None
+        try:
+            from oracle import build_ref
+            if os.path.exists(build_ref.so_path()):
+                ref = build_ref.load()
+        except Exception as e:  # pragma: no cover
+            other["reference_cuda_op_error"] = repr(e)
+        if ref is not None:
+            rf = [(lambda g=g: ref.deformable_aggregation_forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"]))
+                  for g in ss8]
+            other["r50_bs8"]["reference_cuda_op_us"] = time_graph(rf, 6, 2, False, nosync) / 6 * 1e3
+        del ss8
+        torch.cuda.empty_cache()
+        other["r50_bs8_train_anchors"], s_ = fwd_point(syn.R50_LEVELS, 8, TRAIN_ANCHORS)
+        del s_
+        torch.cuda.empty_cache()
+        other["r101_bs1"], s_ = fwd_point(syn.R101_LEVELS, 1, 900, n_sets=2, steps=60)
+        del s_
+        other["r101_bs8"], s_ = fwd_point(syn.R101_LEVELS, 8, 900, n_sets=2, steps=20)
+        del s_
+        torch.cuda.empty_cache()
+        # headline shape: warm L2, backward, reference op
+        dtype = torch.float32 if args.dtype == "f32" else torch.bfloat16
+        sets = [to_device(d, dtype) for d in host]
+        fwd = [(lambda g=g: cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])) for g in sets]
+        roof["fwd_warm_l2_us"] = time_graph(fwd[:1], 100, 10, True, nosync) / 100 * 1e3
         gf = torch.empty_like(sets[0]["feat"], dtype=torch.float32)
         bwd = [(lambda g=g: cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"], gf,
                                           torch.empty_like(g["loc"]), torch.empty_like(g["w"]),
                                           flags=cabi.BWD_OVERWRITE_SMALL | cabi.BWD_ZERO_GRAD_FEAT))
                for g in sets]
-        out["bwd_cold_us"] = t_of(bwd, 40) * 1e3
+        roof["bwd_cold_us"] = time_graph(bwd, 40, 10, True, nosync) / 40 * 1e3
         bwd_nz = [(lambda g=g: cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"], gf,
                                              torch.empty_like(g["loc"]), torch.empty_like(g["w"]),
                                              flags=cabi.BWD_OVERWRITE_SMALL)) for g in sets]
-        out["bwd_cold_no_memset_us"] = t_of(bwd_nz, 40) * 1e3
-    except Exception as e:  # pragma: no cover
-        out["error"] = repr(e)
-    # the unmodified reference CUDA op on this GPU (oracle/_ref, built by oracle/build_ref.py)
-    try:
-        from oracle import build_ref
-        if os.path.exists(build_ref.so_path()) and args.dtype == "f32":
-            ref = build_ref.load()
+        roof["bwd_cold_no_memset_us"] = time_graph(bwd_nz, 40, 10, True, nosync) / 40 * 1e3
+        if ref is not None and args.dtype == "f32":
             rf = [(lambda g=g: ref.deformable_aggregation_forward(g["feat"], g["shape"], g["start"],
                                                                   g["loc"], g["w"])) for g in sets]
-            ms = time_graph(rf, 40, 5, False, nosync) / 40
-            out["reference_cuda_op_fwd_cold_us"] = ms * 1e3
             g = sets[0]
             gfr, glr, gwr = torch.zeros_like(g["feat"]), torch.zeros_like(g["loc"]), torch.zeros_like(g["w"])
             rb = [(lambda g=g: (gfr.zero_(), glr.zero_(), gwr.zero_(),
                                 ref.deformable_aggregation_backward(g["feat"], g["shape"], g["start"],
                                                                     g["loc"], g["w"], g["go"], gfr, glr, gwr)))
                   for g in sets]
-            out["reference_cuda_op_bwd_cold_us"] = time_graph(rb, 20, 3, False, nosync) / 20 * 1e3
+            roof["reference_cuda_op"] = {
+                "what": "the unmodified reference op (ops/src/deformable_aggregation_cuda.cu) rebuilt for sm_100a, "
+                        "same GPU, same inputs, cold L2",
+                "fwd_us": time_graph(rf, 40, 5, False, nosync) / 40 * 1e3,
+                "bwd_us_incl_3_memsets": time_graph(rb, 20, 3, False, nosync) / 20 * 1e3}
     except Exception as e:  # pragma: no cover
-        out["reference_cuda_op_error"] = repr(e)
-    return out
+        other["error"] = repr(e)
+    roof["other_shapes"] = other
 
 
 def main():

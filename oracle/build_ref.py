@@ -82,6 +82,22 @@ def build(force=False, verbose=False):
     return target
 
 
+def stage_python():
+    """Copies the reference's Python files of the hot path (oracle/ref_import.py: FILES) from
+    /root/reference into oracle/_ref/py — git-ignored like the built .so, and like it carried to the GPU
+    box by the snapshot — so that bench.py's reference arm can time the reference's OWN
+    feature_sampling + multi_view_level_fusion (models/blocks.py:215-261) there.  Returns the staged
+    root, or None when neither the reference tree nor an earlier copy exists."""
+    from oracle import ref_import
+    src_root = "/root/reference"
+    if ref_import.available(src_root):
+        for f in ref_import.FILES:
+            dst = os.path.join(ref_import.STAGED_ROOT, f)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(os.path.join(src_root, f), dst)
+    return ref_import.STAGED_ROOT if ref_import.available(ref_import.STAGED_ROOT) else None
+
+
 def load():
     """Import the built reference extension (needs a CUDA device to *run*)."""
     import importlib.util
@@ -96,4 +112,6 @@ def load():
 
 
 if __name__ == "__main__":
+    sys.path.insert(0, os.path.dirname(HERE))
     print(build(force="--force" in sys.argv, verbose=True))
+    print(stage_python())

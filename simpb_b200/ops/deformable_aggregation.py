@@ -1,10 +1,20 @@
 """autograd binding of the op — mirrors
 /root/reference/projects/mmdet3d_plugin/ops/deformable_aggregation.py:7-75."""
+import os
+
 import torch
 from torch.autograd.function import Function, once_differentiable
 
 from .. import cabi
 
+# Opt-in (DFA_PREFILL_GRAD_FEAT=1, read once at import): allocate the feature gradient in forward()
+# and zero-fill it there on a side stream, so the fill overlaps the forward instead of running in front
+# of the backward kernel.  It saves the fill's time on the backward's critical path (about a third of an
+# op-level training step at bs=8) but keeps a feature-table-sized fp32 buffer alive per call from
+# forward to backward (92 MB per sample and layer at R50) and competes with the forward for HBM —
+# hence off by default: like the reference (ops/deformable_aggregation.py:55-57) the buffer then
+# lives only inside backward().
+PREFILL_GRAD_FEAT = os.environ.get("DFA_PREFILL_GRAD_FEAT", "0") == "1"
 
 _SIDE_STREAMS = {}
 
@@ -34,10 +44,10 @@ class DeformableAggregationFunction(Function):
         sampling_location = sampling_location.contiguous().float()
         weights = weights.contiguous().float()
         ctx.grad_feat = ctx.grad_feat_ready = None
-        if ctx.needs_input_grad[0]:
-            # grad_mc_ms_feat is a scatter target and must start from zero (92 MB per sample at
-            # R50): zero it NOW on a side stream, so the fill overlaps this forward and whatever
-            # runs until the backward instead of sitting in front of the backward kernel.
+        if ctx.needs_input_grad[0] and PREFILL_GRAD_FEAT and not torch.cuda.is_current_stream_capturing():
+            # grad_mc_ms_feat is a scatter target and must start from zero: zero it NOW on a side
+            # stream (see PREFILL_GRAD_FEAT above).  Never inside a stream capture: a forward captured
+            # without its backward would leave the side stream un-joined.
             cur, side = torch.cuda.current_stream(mc_ms_feat.device), _side_stream(mc_ms_feat.device)
             ctx.grad_feat = torch.empty(mc_ms_feat.shape, device=mc_ms_feat.device, dtype=torch.float32)
             side.wait_stream(cur)              # the allocator may hand out a block still in use on `cur`
@@ -56,8 +66,9 @@ class DeformableAggregationFunction(Function):
     @once_differentiable
     def backward(ctx, grad_output):
         mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights = ctx.saved_tensors
-        # one memset (grad_feat) instead of the reference's three zeros_like (:55-57): the kernel
-        # writes the two small gradients in full; the one fill left was started in forward()
+        # one memset (grad_feat, issued by the library on this stream right before the kernel) instead
+        # of the reference's three zeros_like (:55-57): the kernel writes the two small gradients in
+        # full.  With PREFILL_GRAD_FEAT the fill was started in forward() instead.
         grad_feat, ctx.grad_feat = ctx.grad_feat, None
         if grad_feat is not None:
             torch.cuda.current_stream(mc_ms_feat.device).wait_event(ctx.grad_feat_ready)
@@ -66,7 +77,7 @@ class DeformableAggregationFunction(Function):
                 grad_output.contiguous().float(), grad_feat=grad_feat,
                 grad_loc=torch.empty_like(sampling_location), grad_w=torch.empty_like(weights),
                 flags=cabi.BWD_OVERWRITE_SMALL)
-        else:   # frozen features (scatter skipped), or a second backward through a retained graph
+        else:   # the default; also frozen features (scatter skipped) and retained graphs
             grad_feat, grad_loc, grad_w = cabi.backward(
                 mc_ms_feat, spatial_shape, scale_start_index, sampling_location, weights,
                 grad_output.contiguous().float(), need_feat=ctx.needs_input_grad[0])

@@ -122,11 +122,15 @@ def rig_op_inputs(bs=1, A=900, P=13, levels=R50_LEVELS, C=256, G=8, seed=0, feat
     c, s = anchor[..., 7, None], anchor[..., 6, None]
     x, y, z = pts.unbind(-1)
     pts = torch.stack([c * x - s * y, s * x + c * y, z], -1) + anchor[..., None, :3]
+    key_points = pts
     homo = torch.cat([pts, torch.ones_like(pts[..., :1])], -1)
     cam = torch.einsum("bkij,bapj->bapki", proj, homo)
     loc = cam[..., :2] / cam[..., 2:3].clamp(min=1e-5) / wh[:, None, None]
     shape, start, num_feat = level_tables(levels, K)
     d = dict(spatial_shape=shape, scale_start_index=start, num_feat=num_feat)
+    # the 3-D key points and camera matrices the locations come from (the reference's grid_sample path
+    # projects them itself, models/blocks.py:215-230)
+    d["key_points"], d["projection_mat"], d["image_wh"] = key_points.contiguous(), proj, wh
     d["mc_ms_feat"] = torch.randn(bs, num_feat, C, generator=gen) if feat else None
     d["sampling_location"] = loc.contiguous()
     d["weights"] = softmax_weights(gen, bs, A, P, K, len(levels), G)
