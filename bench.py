@@ -339,7 +339,9 @@ def make_bucket(dist):
     params = [torch.nn.Parameter(torch.zeros(BUCKET_FLOATS // 3, device="cuda")) for _ in range(3)]
     for p in params:
         p.grad = torch.ones_like(p)
-    return parallel.GradBucket(params, comm_stream=torch.cuda.Stream()) if dist is not None else None
+    # gradients live in the bucket (as in DDP): no pack / unpack copies around the collective
+    return (parallel.GradBucket(params, comm_stream=torch.cuda.Stream(), alias_grads=True)
+            if dist is not None else None)
 
 
 def run_own_arm(args):
@@ -537,7 +539,9 @@ def train_record(args, cabi, dist, world, rank, sync_all, max_over_ranks):
            "timing": "median of %d regions of %d steps, max over ranks" % (reps, steps)}
     if dist is not None:
         bucket = make_bucket(dist)
-        fns = train_step_fns(cabi, sets, outs, bucket)
+        # four steps per CUDA graph: the all-reduce of a step runs under the next step's kernels, only the
+        # last one of a replay is exposed (a captured graph must join its side stream before it ends)
+        fns = train_step_fns(cabi, sets, outs, bucket) * 2
         t = statistics.median(max_over_ranks(time_regions(fns, steps, 4, True, sync_all, bucket.wait, reps)))
         rec["ms_per_step"] = t / steps
 

@@ -49,28 +49,35 @@ def _tables(sizes, num_cams, device):
     return shape, start
 
 
-def feature_maps_format(feature_maps, inverse=False, dtype=None):
+def feature_maps_format(feature_maps, inverse=False, dtype=None, reference_start_index=False):
     """ops/__init__.py:22-92.  Forward direction: a list over levels of [bs, K, C, H_l, W_l] maps
     becomes [col_feats [bs, K*sum(H_l*W_l), C], spatial_shape [K,L,2] int64, scale_start_index
     [K,L] int64] with col_feats[b, start[k,l] + y*W_l + x, c] == maps[l][b,k,c,y,x] — done here by
     ONE transposing kernel per level writing straight into the final buffer (the reference does
     reshape + cat + permute + flatten).  `dtype=torch.bfloat16` emits a bf16 table (extension).
     A list of lists (camera groups with different resolutions) is formatted group by group and
-    concatenated, as the reference does (:56-61).  inverse=True returns the nested list
-    `[[level maps of camera group 0], ...]` of [bs, n_cam, C, H, W] views (:23-54)."""
+    concatenated, as the reference does (:56-61).  DOCUMENTED DEVIATION: the reference concatenates
+    the groups' own scale_start_index tables, each of which restarts at 0 — rows of every group after
+    the first would then be looked up inside the first group's rows (the branch is never called in the
+    reference repository).  Here the start table of a nested list counts rows from the beginning of
+    col_feats, which is what the op needs; `reference_start_index=True` reproduces the reference's
+    integers bit for bit (tests/golden/flatten_nested.npz).  col_feats and spatial_shape are identical
+    either way.  inverse=True returns the nested list `[[level maps of camera group 0], ...]` of
+    [bs, n_cam, C, H, W] views (:23-54); like the reference's it splits by the sizes in spatial_shape
+    only and never reads scale_start_index, so it inverts both kinds of table."""
     if inverse:
         col, shape, start = feature_maps
         K, L = shape.shape[:2]
         sizes = shape.tolist()
-        starts = start.tolist()
         bs, _, C = col.shape
-        groups, k = [], 0
+        groups, k, row0 = [], 0, 0
         while k < K:   # consecutive cameras with identical level sizes form one group
             k1 = k + 1
             while k1 < K and sizes[k1] == sizes[k]:
                 k1 += 1
             per_cam = sum(h * w for h, w in sizes[k])
-            block = col[:, starts[k][0]:starts[k][0] + (k1 - k) * per_cam]
+            block = col[:, row0:row0 + (k1 - k) * per_cam]
+            row0 += (k1 - k) * per_cam
             block = block.reshape(bs, k1 - k, per_cam, C)
             levels, o = [], 0
             for h, w in sizes[k]:
@@ -85,6 +92,8 @@ def feature_maps_format(feature_maps, inverse=False, dtype=None):
         parts = [feature_maps_format(x, dtype=dtype) for x in feature_maps]
         col = torch.cat([p[0] for p in parts], dim=1)
         shape = torch.cat([p[1] for p in parts], dim=0)
+        if reference_start_index:     # ops/__init__.py:60: every group's table restarts at 0
+            return [col, shape, torch.cat([p[2] for p in parts], dim=0)]
         counts = (shape[..., 0] * shape[..., 1]).flatten()
         start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]]).reshape(shape.shape[0], -1)
         return [col, shape, start]

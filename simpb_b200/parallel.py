@@ -42,12 +42,17 @@ class GradBucket:
     """All parameter gradients of a module in ONE flat buffer, averaged across ranks with a single
     all-reduce (DFA: 247,495 fp32 = 0.99 MB per layer — a latency-bound message, so one launch
     instead of one per tensor).  With a CUDA `comm_stream` the all-reduce is enqueued behind an event
-    on the compute stream and overlaps whatever the compute stream does next; `wait()` joins."""
+    on the compute stream and overlaps whatever the compute stream does next; `wait()` joins.
 
-    def __init__(self, params, group=None, comm_stream=None):
+    alias_grads=True makes every parameter's .grad a VIEW of the flat buffer (what DDP does with its
+    buckets): autograd then accumulates straight into the bucket and pack() / unpack() copy nothing.
+    On NCCL the mean is taken by the collective itself (ReduceOp.AVG: no separate division kernel)."""
+
+    def __init__(self, params, group=None, comm_stream=None, alias_grads=False):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.comm_stream = comm_stream
+        self.alias_grads = alias_grads
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, device=ref.device, dtype=ref.dtype)
@@ -55,9 +60,16 @@ class GradBucket:
         for p in self.params:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
+        if alias_grads:
+            for p, v in zip(self.params, self.views):
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
         self._event = None
 
     def pack(self):
+        if self.alias_grads:
+            return
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
@@ -65,28 +77,34 @@ class GradBucket:
                 v.copy_(p.grad)
 
     def unpack(self):
+        if self.alias_grads:
+            return
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 p.grad = v.clone()
             else:
                 p.grad.copy_(v)
 
+    def _reduce(self):
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat.div_(dist.get_world_size(self.group))
+
     def all_reduce_mean(self):
-        """pack → all-reduce(sum) → divide by world size → (after wait) unpack."""
-        world = dist.get_world_size(self.group)
+        """pack → all-reduce (mean) → (after wait) unpack."""
         self.pack()
         if self.comm_stream is not None:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ready)
-                dist.all_reduce(self.flat, group=self.group)
-                self.flat.div_(world)
+                self._reduce()
                 self._event = torch.cuda.Event()
                 self._event.record(self.comm_stream)
         else:
-            dist.all_reduce(self.flat, group=self.group)
-            self.flat.div_(world)
+            self._reduce()
 
     def wait(self):
         if self._event is not None:

@@ -105,6 +105,25 @@ def flatten_case(ops, name, seed, bs, K, C, sizes):
     print(name, col.shape, shape.tolist()[0], start.tolist()[0])
 
 
+def flatten_nested_case(ops, name, seed, bs, C, groups):
+    """A list of camera GROUPS with different resolutions (ops/__init__.py:56-61): the reference formats
+    every group on its own and concatenates — its scale_start_index therefore RESTARTS AT 0 in every
+    group.  groups = [(n_cams, [(H, W), ...]), ...]."""
+    g = torch.Generator().manual_seed(seed)
+    nested = [[torch.randn(bs, k, C, h, w, generator=g) for h, w in sizes] for k, sizes in groups]
+    col, shape, start = ops.feature_maps_format(nested)
+    back = ops.feature_maps_format([col, shape, start], inverse=True)
+    d = dict(col=col.numpy(), shape=shape.numpy(), start=start.numpy(), n_groups=np.int64(len(groups)))
+    for gi, (k, sizes) in enumerate(groups):
+        d["g%d_cams" % gi] = np.int64(k)
+        d["g%d_sizes" % gi] = np.array(sizes, np.int64)
+        for l, m in enumerate(nested[gi]):
+            d["g%d_map%d" % (gi, l)] = m.numpy()
+            assert torch.equal(back[gi][l], m)      # the reference's inverse ignores the start table
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, col.shape, shape.tolist(), start.tolist())
+
+
 def module_case(blocks, name, seed, bs, A, embed, groups, sizes, cams, n_learn, camera_embed,
                 residual):
     torch.manual_seed(seed)
@@ -235,6 +254,10 @@ def module_released_case(blocks, name, seed, n_keep=48):
                         key_points=kp.numpy(), points_2d=uv[:, :, :n_keep].numpy(),
                         weights=w[:, :n_keep].numpy(), out=out[:, :n_keep].numpy(),
                         out_abs_max=np.float64(out.abs().max()))
+    # every anchor's aggregated + projected features (the first 256 channels; the rest of the "cat"
+    # output is the instance feature itself), for the full-size check of the fused forward
+    np.savez_compressed(os.path.join(OUT, name + "_out.npz"), seed=np.int64(seed),
+                        out=out[..., :256].numpy())
     print(name, "out", out.shape, "abs max", float(out.abs().max()), "weights", w.shape)
 
 
@@ -269,6 +292,13 @@ def msda_case(name, seed, bs, Q, M, D, sizes, P):
 if __name__ == "__main__":
     blocks, ops = import_reference()
     sizes = [(8, 12), (4, 6), (2, 3)]
+    if "--round2" in sys.argv:      # only the fixtures added in round 2 (the others are unchanged)
+        flatten_nested_case(ops, "flatten_nested", 11, bs=2, C=8,
+                            groups=[(2, [(6, 10), (3, 5)]), (1, [(4, 6), (2, 3)]), (3, [(6, 10), (3, 5)])])
+        module_released_case(blocks, "module_released_r50", 88)
+        sys.exit(0)
+    flatten_nested_case(ops, "flatten_nested", 11, bs=2, C=8,
+                        groups=[(2, [(6, 10), (3, 5)]), (1, [(4, 6), (2, 3)]), (3, [(6, 10), (3, 5)])])
     flatten_case(ops, "flatten_small", 1, bs=2, K=3, C=16, sizes=sizes)
     # op vs reference fallback with the op's mask multiplied in, fp64 + fp32
     op_case(blocks, "op_masked_f64", 2, 2, 7, 5, 3, sizes, 32, 4, -0.15, 1.15, True, torch.float64)

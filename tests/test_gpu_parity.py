@@ -381,6 +381,31 @@ def test_feature_maps_format_camera_groups_with_different_resolutions():
     assert_close(out, ref, RTOL_F32, "ragged camera groups")
 
 
+def test_nested_camera_groups_vs_reference_fixture(golden_dir):
+    """tests/golden/flatten_nested.npz holds what the REFERENCE's feature_maps_format returns for a list
+    of three camera groups (ops/__init__.py:56-61): col_feats and spatial_shape agree bit for bit; its
+    scale_start_index restarts at 0 in every group, which `reference_start_index=True` reproduces and the
+    default replaces by offsets from the beginning of col_feats (differences)."""
+    from simpb_b200 import feature_maps_format
+    g = np.load(os.path.join(golden_dir, "flatten_nested.npz"))
+    nested = [[torch.from_numpy(g["g%d_map%d" % (gi, l)]).cuda() for l in range(len(g["g%d_sizes" % gi]))]
+              for gi in range(int(g["n_groups"]))]
+    col, shape, start = feature_maps_format(nested, reference_start_index=True)
+    assert torch.equal(col.cpu(), torch.from_numpy(g["col"]))
+    assert torch.equal(shape.cpu(), torch.from_numpy(g["shape"]))
+    assert torch.equal(start.cpu(), torch.from_numpy(g["start"]))
+    assert start.cpu()[2].tolist() == [0, 24]                    # the reference's restart
+    col2, shape2, start2 = feature_maps_format(nested)
+    assert torch.equal(col2, col) and torch.equal(shape2, shape)
+    counts = (shape2[..., 0] * shape2[..., 1]).flatten().cpu()
+    assert start2.cpu().flatten().tolist() == (counts.cumsum(0) - counts).tolist()
+    for tables in ([col, shape, start], [col2, shape2, start2]):   # the inverse reads sizes only
+        back = feature_maps_format(tables, inverse=True)
+        assert len(back) == len(nested)
+        for a, b in zip(back, nested):
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
 def test_border_values_are_excluded():
     """loc exactly 0 or 1 is masked (exclusive test, …_cuda.cu:168-171)."""
     from simpb_b200 import cabi
@@ -609,6 +634,44 @@ def test_against_reference_cuda_op_r50():
         assert_close(gf, rgf, RTOL_F32, "grad_feat vs reference op")
         assert_close(gw, rgw, RTOL_F32, "grad_weights vs reference op")
         assert_close(gl, rgl, 2 * RTOL_F32, "grad_loc vs reference op")
+
+
+def _vs_reference_op(g, what, loc_tol=2 * RTOL_F32):
+    from simpb_b200 import cabi
+    ref_ext = _ref_ext()
+    out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    rout = ref_ext.deformable_aggregation_forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    assert_close(out, rout, RTOL_F32, what + ": forward vs reference op")
+    del out, rout
+    gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    rgf = torch.zeros_like(g["feat"]); rgl = torch.zeros_like(g["loc"]); rgw = torch.zeros_like(g["w"])
+    ref_ext.deformable_aggregation_backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
+                                            rgf, rgl, rgw)
+    assert_close(gf, rgf, RTOL_F32, what + ": grad_feat vs reference op")
+    assert_close(gw, rgw, RTOL_F32, what + ": grad_weights vs reference op")
+    assert_close(gl, rgl, loc_tol, what + ": grad_loc vs reference op")
+
+
+def test_training_shape_bs8_all_gradients_vs_reference_cuda_op():
+    """bs=8 x 900 anchors (the window-merging forward is the default there) and the backward's three
+    gradients, every element, against the unmodified reference binary on the same inputs."""
+    from simpb_b200 import synthetic
+    _vs_reference_op(dev(synthetic.rig_op_inputs(bs=8, seed=61)), "R50 bs=8")
+
+
+@pytest.mark.parametrize("corner", ["A3600_P32", "R101_bs8"])
+def test_sweep_corners_vs_reference_cuda_op(corner):
+    """The extreme points of BASELINE.json configs #4 / #5 (tools/op_sweep.py times them): 3,600
+    anchors x 32 key points at bs=1, and R101 1408x512 maps at bs=8."""
+    from simpb_b200 import synthetic
+    if corner == "A3600_P32":
+        d = synthetic.rig_op_inputs(bs=1, A=3600, P=32, seed=62)
+    else:
+        d = synthetic.rig_op_inputs(bs=8, levels=synthetic.R101_LEVELS, seed=63, feat=False)
+        gen = torch.Generator().manual_seed(63)
+        d["mc_ms_feat"] = torch.randn(8, d["num_feat"], 256, generator=gen)
+    _vs_reference_op(dev(d), corner)
+    torch.cuda.empty_cache()
 
 
 def test_reference_binary_pins_indices_and_masks():

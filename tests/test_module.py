@@ -207,6 +207,21 @@ def test_released_config_full_size_matches_the_reference_module():
     sel = (ref_uv.abs() < 4).all(-1)
     assert (loc[:, :n].cpu() - ref_uv)[sel].abs().max() < 1e-4
     assert_close(out, want, RTOL_F32, "module output, released config")
+    # all 900 anchors against the REFERENCE MODULE's own output (grid_sample path, module_released_r50_out
+    # .npz): anchors whose samples stay clear of grid_sample's half-pixel border band — where the op's
+    # exclusive (0,1) mask and grid_sample differ by design — must agree to 1e-5
+    ref_out = torch.from_numpy(load_golden("module_released_r50_out")["out"])          # [1,900,256]
+    bx, by = 0.5 / 22 + 1e-6, 0.5 / 8 + 1e-6      # half a pixel of the coarsest level (8 x 22)
+    l = loc.cpu()
+    x, y = l[..., 0], l[..., 1]
+    inside = (x > 0) & (x < 1) & (y > 0) & (y < 1)
+    in_band = (x > -bx) & (x < 1 + bx) & (y > -by) & (y < 1 + by)      # grid_sample still sees the map
+    risky = (in_band & ~inside).flatten(2).any(-1)[0]                                   # [900] anchors
+    clean = ~risky
+    assert int(clean.sum()) > 600
+    scale = ref_out.abs().max()
+    err = (out[..., :256].cpu() - ref_out)[0, clean].abs().max() / scale
+    assert float(err) <= RTOL_F32, "fused forward vs reference module, %d clean anchors: %.3e" % (int(clean.sum()), err)
 
 
 @pytest.mark.gpu

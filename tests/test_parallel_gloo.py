@@ -38,7 +38,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, alias=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -54,11 +54,18 @@ def _worker(rank, world, port, out_dir):
         out = torch.from_numpy(oracle.forward(mine["mc_ms_feat"], mine["spatial_shape"],
                                               mine["scale_start_index"], mine["sampling_location"],
                                               mine["weights"])).float()
+        bucket = None
+        if alias:   # DDP style: the gradients are views of the flat bucket before the backward runs
+            bucket = parallel.GradBucket(lin.parameters(), alias_grads=True)
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
         y = lin(out)
         # loss = sum over the GLOBAL batch / global batch size: each rank contributes its share
         loss = y.square().sum() / 5.0
         loss.backward()
-        bucket = parallel.GradBucket(lin.parameters())
+        if alias:
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+        else:
+            bucket = parallel.GradBucket(lin.parameters())
         # DDP semantics: mean over ranks of per-rank gradients; scale so the sum is what we want
         for p in lin.parameters():
             p.grad.mul_(world)
@@ -79,9 +86,13 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_sharded_op_plus_bucket_allreduce_equals_single_process(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("alias", [False, True])
+def test_sharded_op_plus_bucket_allreduce_equals_single_process(tmp_path, alias):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), alias), nprocs=world, join=True)
     got = np.load(os.path.join(str(tmp_path), "rank0.npz"))
     torch.manual_seed(0)
     lin = torch.nn.Linear(16, 24)

@@ -2,6 +2,10 @@
 anchors 900 -> 3600 x key points 13 -> 32 x fp32 / bf16 features (bs=1, R50 maps), forward and
 backward, against the unmodified reference CUDA op (oracle/_ref, fp32 only) on the same inputs.
 Cold L2 (rotating input sets), CUDA events inside a CUDA graph.  One JSON line per point.
+Every point is also a PARITY point: forward output and the three gradients are compared with the
+reference binary on the same inputs (max|x - ref| / max|ref| <= 1e-5; 2e-5 for the location gradient,
+whose reference value comes from 1024-way float atomics) and the script exits non-zero on a miss.
+bfloat16 points are checked against the reference op run on the bf16-rounded table.
     python tools/op_sweep.py [--quick]
 """
 import json
@@ -24,6 +28,29 @@ try:
         ref = build_ref.load()
 except Exception:
     ref = None
+
+
+def rel(x, r):
+    return float((x.double() - r.double()).abs().max() / r.double().abs().max().clamp_min(1e-30))
+
+
+def parity(g):
+    """Forward + three gradients of our op against the reference binary on one input set."""
+    if ref is None or g["loc"].shape[0] * g["loc"].shape[1] * g["loc"].shape[2] > 349525:
+        return None
+    f32 = g["feat"].float()
+    out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"])
+    gf, gl, gw = cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"])
+    rout = ref.deformable_aggregation_forward(f32, g["shape"], g["start"], g["loc"], g["w"])
+    rgf, rgl, rgw = torch.zeros_like(f32), torch.zeros_like(g["loc"]), torch.zeros_like(g["w"])
+    ref.deformable_aggregation_backward(f32, g["shape"], g["start"], g["loc"], g["w"], g["go"], rgf, rgl, rgw)
+    e = {"out": rel(out, rout), "grad_feat": rel(gf, rgf), "grad_loc": rel(gl, rgl), "grad_w": rel(gw, rgw)}
+    del rgf, gf
+    ok = e["out"] <= 1e-5 and e["grad_feat"] <= 1e-5 and e["grad_w"] <= 1e-5 and e["grad_loc"] <= 2e-5
+    return dict(rel_err=e, ok=ok)
+
+
+FAILED = []
 
 
 def point(name, levels, bs, A, P, dt):
@@ -61,6 +88,11 @@ def point(name, levels, bs, A, P, dt):
         rec["reference_op_bwd_us"] = round(bench.time_graph(rb, 6, 1, False, sync) / 6 * 1e3, 1)
         rec["fwd_speedup_vs_reference_op"] = round(rec["reference_op_fwd_us"] / rec["fwd_us"], 1)
         rec["bwd_speedup_vs_reference_op"] = round(rec["reference_op_bwd_us"] / rec["bwd_us_incl_fill"], 1)
+    par = parity(sets[0])
+    if par is not None:
+        rec["parity_vs_reference_op"] = par
+        if not par["ok"]:
+            FAILED.append((name, bs, A, P, dt, par["rel_err"]))
     print(json.dumps(rec), flush=True)
     del sets, outs, gf
     torch.cuda.empty_cache()
@@ -79,3 +111,6 @@ if not quick:
                 if (A, P, dt) == (900, 13, "f32"):
                     continue
                 point("sweep", R50, 1, A, P, dt)
+if FAILED:
+    print("PARITY FAILED:", FAILED, file=sys.stderr)
+    sys.exit(1)
