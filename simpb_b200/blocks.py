@@ -139,7 +139,7 @@ class SparseBox3DKeyPointsGenerator(nn.Module):
         cos, sin = anchor[..., None, COS_YAW], anchor[..., None, SIN_YAW]
         pts = torch.stack([cos * pts[..., 0] - sin * pts[..., 1],
                            sin * pts[..., 0] + cos * pts[..., 1], pts[..., 2]], dim=-1)
-        pts = pts + anchor[..., None, [X, Y, Z]]
+        pts = pts + anchor[..., None, X:Z + 1]
         if (cur_timestamp is None or temp_timestamps is None or T_cur2temp_list is None
                 or len(temp_timestamps) == 0):
             return pts
@@ -162,7 +162,7 @@ class SparseBox3DKeyPointsGenerator(nn.Module):
             T = T.to(anchor.dtype)[:, None]
             vel = anchor[..., VX:]
             nv = vel.shape[-1]
-            center = anchor[..., [X, Y, Z]]
+            center = anchor[..., X:Z + 1]
             if time_intervals is not None:
                 dt = time_intervals[i]
             elif src_timestamp is not None and dst_timestamps is not None:
@@ -172,9 +172,9 @@ class SparseBox3DKeyPointsGenerator(nn.Module):
             if dt is not None:
                 center = center - (vel.transpose(0, -1) * dt).transpose(0, -1)
             center = (T[..., :3, :3] @ center[..., None]).squeeze(-1) + T[..., :3, 3]
-            yaw = (T[..., :2, :2] @ anchor[..., [COS_YAW, SIN_YAW], None]).squeeze(-1)
+            yaw = (T[..., :2, :2] @ anchor[..., SIN_YAW:COS_YAW + 1].flip(-1)[..., None]).squeeze(-1)
             vel = (T[..., :nv, :nv] @ vel[..., None]).squeeze(-1)
-            out.append(torch.cat([center, anchor[..., [W, L, H]], yaw, vel], dim=-1))
+            out.append(torch.cat([center, anchor[..., W:H + 1], yaw, vel], dim=-1))
         return out
 
     @staticmethod

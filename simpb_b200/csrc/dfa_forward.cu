@@ -639,6 +639,7 @@ __global__ void dfa_debug_indices_kernel(const int *__restrict__ shape, const in
 }  // namespace
 
 #include "dfa_forward_win.cuh"
+#include "dfa_forward_gs.cuh"
 
 namespace {
 
@@ -673,6 +674,17 @@ int launch_fwd_t(const void *feat, const int *shape, const int *start, const flo
 // quarter as long.  Measured: 19.2 -> 17.9 us at bs=1 / 900 anchors, 24.8 -> 23.5 us at 1220 anchors,
 // 31.6 -> 30.3 us at bs=2, neutral from bs=4 on.  DFA_FWD_SPLIT: 0 = never, 1 = as described
 // (default), 2 / 3 = every anchor two / four ways (experiments: par / slower).
+// SM count of the current device, queried once per device and process.
+inline int device_sm_count() {
+  static std::atomic<int> sm_count[64];  // 0 = not queried yet; racing threads store the same value
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  int sms = sm_count[dev].load(std::memory_order_relaxed);
+  if (!sms && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+    sm_count[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
+
 template <typename T>
 void last_wave_split(const Dims &d, int vpr, int ctas_per_sm, long long &split_from, int &split_log2,
                      long long &grid) {
@@ -682,12 +694,8 @@ void last_wave_split(const Dims &d, int vpr, int ctas_per_sm, long long &split_f
   const int mode = DFA_KNOB("DFA_FWD_SPLIT", 1);
   const int max_log2 = ((d.C / 4) % VEC == 0 && vpr >= 4) ? 2 : (((d.C / 2) % VEC == 0 && vpr >= 2) ? 1 : 0);
   if (mode == 1 && max_log2 == 2) {
-    static std::atomic<int> sm_count[64];  // 0 = not queried yet; racing threads store the same value
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
-      int sms = sm_count[dev].load(std::memory_order_relaxed);
-      if (!sms && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
-        sm_count[dev].store(sms, std::memory_order_relaxed);
+    const int sms = device_sm_count();
+    {
       const long long slots = static_cast<long long>(sms) * ctas_per_sm;
       const long long rem = slots > 0 ? total % slots : 0;  // anchors of the last, partial wave
       const int frac = DFA_KNOB("DFA_FWD_SPLIT_FRAC", 2);  // split when the last wave is at most 1/frac full
@@ -756,6 +764,41 @@ int launch_fwd_win(const void *feat, const int *shape, const int *start, const f
   return static_cast<int>(cudaGetLastError());
 }
 
+// Group-sliced, anchor-pooled kernel: the grid is a whole number of waves of resident CTAs; a block of
+// M anchors x G group CTAs.  DFA_FWD_GS_M = anchors per block the launcher aims at (default 8).
+template <typename T, int LPS, int U, bool TMA>
+int launch_fwd_gs(const void *feat, const int *shape, const int *start, const float *loc, const float *w,
+                  float *out, const Dims &d, int interleave, cudaStream_t st) {
+  constexpr int MINB = 6;
+  auto kern = dfa_fwd_gs_kernel<T, LPS, U, TMA, MINB>;
+  const long long total = static_cast<long long>(d.bs) * d.A;
+  const int sms = device_sm_count();
+  if (sms <= 0) return DFA_ERR_UNSUPPORTED;
+  int m_target = DFA_KNOB("DFA_FWD_GS_M", 8);
+  m_target = m_target < 1 ? 1 : (m_target > GS_MMAX - 1 ? GS_MMAX - 1 : m_target);
+  for (int cps = MINB; cps >= 1; --cps) {
+    const long long bpw = static_cast<long long>(sms) * cps / d.G;  // blocks per wave
+    if (bpw < 1) return DFA_ERR_UNSUPPORTED;
+    long long waves = (2 * total + bpw * m_target) / (2 * bpw * m_target);  // nearest whole number
+    if (waves < 1) waves = 1;
+    long long nblocks = waves * bpw < total ? waves * bpw : total;
+    long long mmax = (total + nblocks - 1) / nblocks;
+    if (mmax > GS_MMAX) {  // far fewer resident CTAs than expected: more waves of full-size blocks
+      nblocks = (total + GS_MMAX - 1) / GS_MMAX;
+      mmax = (total + nblocks - 1) / nblocks;
+    }
+    const GsLayout lay = gs_layout(d.P, d.K, d.L, static_cast<int>(mmax), d.C / d.G);
+    if ((static_cast<long long>(lay.total) + 1024) * cps > 227ll * 1024 && cps > 1) continue;
+    if (8ll * d.P * d.K * mmax >= (1ll << 20) || nblocks * d.G >= (1ll << 31)) return DFA_ERR_UNSUPPORTED;
+    if (int rc = set_smem(kern, lay.total)) return rc;
+    kern<<<static_cast<unsigned int>(nblocks * d.G), GS_NT, lay.total, st>>>(
+        static_cast<const T *>(feat), shape, start, loc, w, out, d, static_cast<int>(nblocks),
+        static_cast<int>(mmax), interleave);
+    return static_cast<int>(cudaGetLastError());
+  }
+  return DFA_ERR_UNSUPPORTED;
+}
+
 template <typename T>
 int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
                   const float *w, float *out, const Dims &d, cudaStream_t st) {
@@ -796,6 +839,26 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
         default: return WIN(4, 8);
       }
 #undef WIN
+    }
+  }
+  if (variant >= 50 && variant < 60) {  // group-sliced, anchor-pooled kernel
+    const int lps = gs_lps<T>(d, feat, out);
+    if (lps) {
+      const bool tma = tma_ok(d, loc, w);
+      const int il = variant == 51 ? 1 : 0;
+      const int u = DFA_KNOB("DFA_FWD_GS_U", 4);
+#define GS2(LPS, U)                                                                          \
+  (tma ? launch_fwd_gs<T, LPS, U, true>(feat, shape, start, loc, w, out, d, il, st)            \
+       : launch_fwd_gs<T, LPS, U, false>(feat, shape, start, loc, w, out, d, il, st))
+#define GS(LPS) (u == 2 ? GS2(LPS, 2) : u == 6 ? GS2(LPS, 6) : GS2(LPS, 4))
+      switch (lps) {
+        case 8: return GS(8);
+        case 4: return GS(4);
+        case 2: return GS2(2, 4);
+        default: return GS2(1, 4);
+      }
+#undef GS
+#undef GS2
     }
   }
   const int rvariant = variant >= 5 ? 1 : variant;

@@ -1,0 +1,493 @@
+"""SimPB+ R50 decoder FRAME for the frames/sec figure of BASELINE.json config #2.
+
+What is timed there is the whole inference frame of the released configuration
+(/root/reference/projects/configs/simpb_nus_r50_img_704x256.py): six 704x256 images -> ResNet-50
+-> FPN -> the multi-camera / multi-scale feature table -> the 50-operation decoder of SimPBHead
+(models/simpb_head.py:323-747, operation order config :58-72) over 900 3-D anchors, of which 600 are
+temporal instances carried over from the previous frame (models/instance_bank.py:79-167).
+
+This file restates that frame's STRUCTURE — the same operation order, tensor shapes, layer types
+and widths, query counts produced by the same projection-based allocation — around this repository's
+two gather modules (`blocks.DeformableFeatureAggregation` for "deformable",
+`msda.QueryGroupMultiScaleDeformableAttention` for "qg_cross_attn") and `feature_maps_format`.
+Weights are random (there is no checkpoint and no network here), inputs synthetic, inference only (no
+denoising queries, no losses).  It is a measurement harness: the reference head itself needs mmcv /
+mmdet / mmdet3d and cannot be imported in this image, so this file is NOT numerically pinned to it —
+the parity-tested pieces are the gather modules it calls.  Everything else is plain PyTorch
+(nn.MultiheadAttention, nn.Linear, torchvision's ResNet-50), as in the reference.
+
+Reference lines restated by each piece are cited at the piece.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import blocks, msda, synthetic
+from .ops import feature_maps_format
+
+X, Y, Z, W, L, H, SIN_YAW, COS_YAW, VX = 0, 1, 2, 3, 4, 5, 6, 7, 8      # core/box3d.py
+
+# config :58-72
+SINGLE_2D = ["allocation", "qg_self_attn", "norm", "qg_cross_attn", "ffn", "norm", "refine2d", "aggregation", "refine3d"]
+LAYER_3D = ["temp_gnn", "gnn", "norm", "deformable", "ffn", "norm", "refine3d"]
+LAYER_2D = ["temp_gnn", "allocation", "qg_self_attn", "norm", "qg_cross_attn", "ffn", "norm", "refine2d",
+            "aggregation", "refine3d"]
+OPERATION_ORDER = SINGLE_2D + LAYER_3D + LAYER_2D + LAYER_3D + LAYER_2D + LAYER_3D
+
+
+def linear_relu_ln(embed_dims, in_loops, out_loops, input_dims=None):
+    """models/blocks.py:32-42."""
+    input_dims = embed_dims if input_dims is None else input_dims
+    layers = []
+    for _ in range(out_loops):
+        for _ in range(in_loops):
+            layers += [nn.Linear(input_dims, embed_dims), nn.ReLU(inplace=True)]
+            input_dims = embed_dims
+        layers.append(nn.LayerNorm(embed_dims))
+    return layers
+
+
+class Scale(nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        self.scale = nn.Parameter(torch.ones(n))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+class SparseBox3DEncoder(nn.Module):
+    """models/detection3d/blocks.py:24-74, released settings: embed_dims [128, 32, 32, 64], mode
+    "cat", no output fc, in_loops 1, out_loops 4."""
+
+    def __init__(self, dims=(128, 32, 32, 64)):
+        super().__init__()
+        self.pos_fc = nn.Sequential(*linear_relu_ln(dims[0], 1, 4, 3))
+        self.size_fc = nn.Sequential(*linear_relu_ln(dims[1], 1, 4, 3))
+        self.yaw_fc = nn.Sequential(*linear_relu_ln(dims[2], 1, 4, 2))
+        self.vel_fc = nn.Sequential(*linear_relu_ln(dims[3], 1, 4, 3))
+
+    def forward(self, box):
+        return torch.cat([self.pos_fc(box[..., X:Z + 1]), self.size_fc(box[..., W:H + 1]),
+                          self.yaw_fc(box[..., SIN_YAW:COS_YAW + 1]), self.vel_fc(box[..., VX:VX + 3])], dim=-1)
+
+
+def pos2posemb2d(pos, num_pos_feats=128, temperature=10000):
+    """models/utils.py:42-62 (two-coordinate branch)."""
+    pos = pos * (2 * math.pi)
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=pos.device)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    px, py = pos[..., 0, None] / dim_t, pos[..., 1, None] / dim_t
+    px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=-1).flatten(-2)
+    py = torch.stack((py[..., 0::2].sin(), py[..., 1::2].cos()), dim=-1).flatten(-2)
+    return torch.cat((py, px), dim=-1)
+
+
+class SparseBox2DEncoder(nn.Module):
+    """models/detection2d/blocks.py:20-62, with_sin_embed."""
+
+    def __init__(self, embed_dims=256):
+        super().__init__()
+        self.query_embeddings2d = nn.Sequential(*linear_relu_ln(embed_dims, 1, 2, 256))
+
+    def forward(self, box_2d):
+        return self.query_embeddings2d(pos2posemb2d(box_2d[..., :2]))
+
+
+class Refine3D(nn.Module):
+    """SparseBox3DRefinementModule, models/detection3d/blocks.py:77-155 (refine_yaw, quality)."""
+
+    def __init__(self, embed_dims=256, num_cls=10):
+        super().__init__()
+        self.layers = nn.Sequential(*linear_relu_ln(embed_dims, 2, 2), nn.Linear(embed_dims, 11), Scale(11))
+        self.cls_layers = nn.Sequential(*linear_relu_ln(embed_dims, 1, 2), nn.Linear(embed_dims, num_cls))
+        self.quality_layers = nn.Sequential(*linear_relu_ln(embed_dims, 1, 2), nn.Linear(embed_dims, 2))
+        nn.init.constant_(self.cls_layers[-1].bias, -math.log((1 - 0.01) / 0.01))
+
+    def forward(self, feature, anchor, anchor_embed, time_interval, return_cls=True):
+        f = feature + anchor_embed
+        out = self.layers(f)
+        state = out[..., :VX] + anchor[..., :VX]                       # X..COS_YAW are all refined
+        vel = out[..., VX:] / time_interval[:, None, None] + anchor[..., VX:]
+        out = torch.cat([state, vel], dim=-1)
+        if not return_cls:
+            return out, None, None
+        return out, self.cls_layers(feature), self.quality_layers(f)
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    x = x.clamp(0, 1)
+    return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
+
+
+class Refine2D(nn.Module):
+    """SparseBox2DRefinementModule, models/detection2d/blocks.py:64-144 (class + alpha branches)."""
+
+    def __init__(self, embed_dims=256, num_cls=10):
+        super().__init__()
+        self.layers = nn.Sequential(*linear_relu_ln(embed_dims, 2, 2), nn.Linear(embed_dims, 4), Scale(4))
+        self.cls_layers = nn.Sequential(*linear_relu_ln(embed_dims, 1, 2), nn.Linear(embed_dims, num_cls))
+        self.alpha_layers = nn.Sequential(*linear_relu_ln(embed_dims, 1, 2), nn.Linear(embed_dims, 2), Scale(2))
+
+    def forward(self, feature, anchor2d, anchor_embed2d):
+        out = self.layers(feature + anchor_embed2d)
+        out = torch.cat([out[..., :2] + inverse_sigmoid(anchor2d[..., :2]), out[..., 2:]], dim=-1)
+        return out.sigmoid(), self.cls_layers(feature), self.alpha_layers(feature)
+
+
+class AsymmetricFFN(nn.Module):
+    """models/blocks.py:329-393: pre-norm on the 512 concatenated channels, 512 -> 1024 -> 256, identity
+    through a 512 -> 256 fc."""
+
+    def __init__(self, in_channels=512, embed_dims=256, hidden=1024):
+        super().__init__()
+        self.pre_norm = nn.LayerNorm(in_channels)
+        self.layers = nn.Sequential(nn.Linear(in_channels, hidden), nn.ReLU(inplace=True), nn.Linear(hidden, embed_dims))
+        self.identity_fc = nn.Linear(in_channels, embed_dims)
+
+    def forward(self, x):
+        x = self.pre_norm(x)
+        return self.identity_fc(x) + self.layers(x)
+
+
+class DynamicQueryAllocation(nn.Module):
+    """models/allocation.py:22-143, inference branch, vectorised over the batch: project every 3-D anchor's
+    centre and eight box corners into the six cameras; an anchor gets a 2-D query in every camera that sees
+    its centre or one of its corners.  Queries are laid out camera by camera (query_groups); trans_matrix
+    [bs, n2d, A] carries 3-D features to the 2-D queries (matmul) and back."""
+
+    def __init__(self, limit_anchor_size=(35.0, 35.0, 10.0)):
+        super().__init__()
+        self.register_buffer("limit", torch.tensor(limit_anchor_size), persistent=False)
+        c = torch.stack(torch.meshgrid(*[torch.arange(2.0)] * 3, indexing="ij"), -1).reshape(8, 3) - 0.5
+        self.register_buffer("corners_norm", c, persistent=False)
+
+    def forward(self, anchor, proj, image_wh, cap=None):
+        """cap=None: query counts follow the data (one host sync, as in the reference).  cap=N: every
+        camera owns N query slots (static shapes, no sync: the frame can be captured in a CUDA graph);
+        unused slots are marked invalid in the returned mask and never feed a valid query or anchor."""
+        bs, A = anchor.shape[:2]
+        K = proj.shape[1]
+        if isinstance(image_wh, (tuple, list)):
+            img_w, img_h = float(image_wh[0]), float(image_wh[1])
+        else:
+            img_w, img_h = float(image_wh[0, 0, 0]), float(image_wh[0, 0, 1])
+        cs, sn = anchor[..., COS_YAW], anchor[..., SIN_YAW]
+        size = anchor[..., W:H + 1].exp().minimum(self.limit)
+        c = size[:, :, None] * self.corners_norm                                       # [bs,A,8,3]
+        corners = torch.stack([cs[..., None] * c[..., 0] - sn[..., None] * c[..., 1],
+                               sn[..., None] * c[..., 0] + cs[..., None] * c[..., 1], c[..., 2]], -1)
+        pts = torch.cat([corners + anchor[:, :, None, :3], anchor[:, :, None, :3]], dim=2)        # [bs,A,9,3]
+        homo = torch.cat([pts, torch.ones_like(pts[..., :1])], -1)
+        p2d = torch.einsum("bkij,banj->bakni", proj, homo)                             # [bs,A,K,9,4]
+        depth = p2d[..., 2:3]
+        uv = p2d[..., :2] / depth.clamp(1e-5)
+        inside = (uv[..., 0] > 0) & (uv[..., 0] < img_w) & (uv[..., 1] > 0) & (uv[..., 1] < img_h)
+        center_valid = inside[..., 8]
+        corner_valid = (inside[..., :8] & (depth[..., :8, 0] > 0)).any(-1)
+        cu = uv[..., :8, :]
+        x_min, x_max = cu[..., 0].amin(-1).clamp(0, img_w), cu[..., 0].amax(-1).clamp(0, img_w)
+        y_min, y_max = cu[..., 1].amin(-1).clamp(0, img_h), cu[..., 1].amax(-1).clamp(0, img_h)
+        centers = torch.stack([(x_min + x_max) / 2, (y_min + y_max) / 2], -1)
+        centers = torch.where(center_valid[..., None], uv[..., 8, :], centers)
+        mask = (center_valid | corner_valid).permute(0, 2, 1)                          # [bs,K,A]
+        if cap is not None:
+            return self.static_slots(anchor, mask, centers, depth, center_valid, img_w, img_h, cap)
+        counts = mask.sum(-1)                                                          # [bs,K]
+        group = counts.max(0).values.tolist()            # host sync, as in the reference (allocation.py:94)
+        starts = [0]
+        for g in group:
+            starts.append(starts[-1] + g)
+        n2d = starts[-1]
+        query_groups = [(starts[i], starts[i + 1]) for i in range(K)]
+        # slot of every (b, k, a) pair inside its camera's group, in anchor order
+        slot = mask.cumsum(-1) - 1 + torch.tensor(starts[:K], device=anchor.device)[None, :, None]
+        b_idx, k_idx, a_idx = torch.nonzero(mask, as_tuple=True)
+        q_idx = slot[b_idx, k_idx, a_idx]
+        ref = anchor.new_zeros(bs, n2d, 2)
+        dep = anchor.new_zeros(bs, n2d, 1)
+        ref[b_idx, q_idx] = centers.permute(0, 2, 1, 3)[b_idx, k_idx, a_idx] / anchor.new_tensor([img_w, img_h])
+        dep[b_idx, q_idx] = depth[..., 8, :].permute(0, 2, 1, 3)[b_idx, k_idx, a_idx].abs()
+        trans = anchor.new_zeros(bs, n2d, A)
+        trans[b_idx, q_idx, a_idx] = 1.0
+        center = anchor.new_zeros(bs, n2d, A)
+        cv = center_valid.permute(0, 2, 1)[b_idx, k_idx, a_idx]
+        center[b_idx[cv], q_idx[cv], a_idx[cv]] = 1.0
+        return ref, dep, trans, center, query_groups, None
+
+    def wh_tensor(self, like, img_w, img_h):
+        key = (img_w, img_h, like.device, like.dtype)
+        if getattr(self, "_inv_wh_key", None) != key:      # built once: no host-to-device copy under capture
+            self._inv_wh_key, self._inv_wh = key, like.new_tensor([img_w, img_h])
+        return self._inv_wh
+
+    def static_slots(self, anchor, mask, centers, depth, center_valid, img_w, img_h, cap):
+        bs, K, A = mask.shape
+        n2d = K * cap
+        slot = mask.cumsum(-1) - 1
+        keep = mask & (slot < cap)
+        q = torch.where(keep, slot + torch.arange(K, device=anchor.device)[None, :, None] * cap,
+                        torch.full_like(slot, n2d))                                    # dump row n2d
+        keepf = keep.to(anchor.dtype)
+        trans = anchor.new_zeros(bs, n2d + 1, A)
+        center = anchor.new_zeros(bs, n2d + 1, A)
+        cvf = (keep & center_valid.permute(0, 2, 1)).to(anchor.dtype)
+        for k in range(K):          # every anchor has at most one slot per camera
+            trans.scatter_(1, q[:, k, None, :], keepf[:, k, None, :])
+            center.scatter_(1, q[:, k, None, :], cvf[:, k, None, :])
+        qf = q.reshape(bs, K * A, 1)
+        ref = anchor.new_zeros(bs, n2d + 1, 2).scatter_(
+            1, qf.expand(-1, -1, 2), (centers.permute(0, 2, 1, 3) / self.wh_tensor(anchor, img_w, img_h)).reshape(bs, K * A, 2))
+        dep = anchor.new_zeros(bs, n2d + 1, 1).scatter_(
+            1, qf, depth[..., 8, :].permute(0, 2, 1, 3).abs().reshape(bs, K * A, 1))
+        valid = anchor.new_zeros(bs, n2d + 1).scatter_(1, qf[..., 0], keepf.reshape(bs, K * A)) > 0
+        groups = [(k * cap, (k + 1) * cap) for k in range(K)]
+        return ref[:, :n2d], dep[:, :n2d], trans[:, :n2d], center[:, :n2d], groups, valid[:, :n2d]
+
+
+class ReWeight(nn.Module):
+    """models/aggregation.py:10-41 (trans, with_pos)."""
+
+    def __init__(self, c_dim=257, f_dim=256):
+        super().__init__()
+        self.reduce = nn.Sequential(nn.Linear(c_dim, f_dim), nn.ReLU())
+        self.alpha = nn.Sequential(nn.Linear(f_dim, 1), nn.Sigmoid())
+
+    def forward(self, query, query_pos, parameter, trans_matrix):
+        m = (trans_matrix * self.alpha(self.reduce(parameter))).permute(0, 2, 1)       # [bs,A,n2d]
+        div = m.sum(-1, keepdim=True).clamp(1e-5)
+        return torch.matmul(m, query) / div, torch.matmul(m, query_pos) / div
+
+
+class FrameDecoder(nn.Module):
+    """SimPBHead at inference (models/simpb_head.py:323-747) with the instance bank
+    (models/instance_bank.py:79-167) folded in."""
+
+    def __init__(self, embed_dims=256, num_groups=8, num_anchor=900, num_temp=600, num_cams=6, num_levels=4,
+                 num_single_frame_decoder=1, confidence_decay=0.6, seed=0, static_queries=None):
+        super().__init__()
+        self.static_queries = static_queries     # 2-D query slots per camera (None: data-dependent, eager only)
+        self.embed_dims, self.num_anchor, self.num_temp = embed_dims, num_anchor, num_temp
+        self.num_single_frame_decoder, self.confidence_decay = num_single_frame_decoder, confidence_decay
+        gen = torch.Generator().manual_seed(seed)
+        # instance bank: k-means anchors in the reference (a data file); rig-distributed ones here
+        self.register_buffer("anchor", synthetic.rig_anchors(gen, 1, num_anchor)[0])
+        self.instance_feature = nn.Parameter(torch.randn(num_anchor, embed_dims, generator=gen) * 0.1,
+                                             requires_grad=False)
+        self.anchor_handler = blocks.SparseBox3DKeyPointsGenerator(embed_dims=embed_dims)
+        self.anchor_encoder = SparseBox3DEncoder()
+        self.anchor_encoder2d = SparseBox2DEncoder(embed_dims)
+        # decouple_attn / decouple_attn2d (simpb_head.py:176-200): attention runs on [feature, embed] = 512
+        self.fc_before, self.fc_after = nn.Linear(embed_dims, 2 * embed_dims, bias=False), nn.Linear(2 * embed_dims, embed_dims, bias=False)
+        self.fc_before2d, self.fc_after2d = nn.Linear(embed_dims, 2 * embed_dims, bias=False), nn.Linear(2 * embed_dims, embed_dims, bias=False)
+        mha = lambda: nn.MultiheadAttention(2 * embed_dims, num_groups, batch_first=True)   # noqa: E731
+        kps = dict(type="SparseBox3DKeyPointsGenerator", num_learnable_pts=6, fix_scale=synthetic.FIX_SCALE)
+        layers = []
+        for op in OPERATION_ORDER:
+            if op in ("gnn", "temp_gnn", "qg_self_attn"):
+                layers.append(mha())
+            elif op == "norm":
+                layers.append(nn.LayerNorm(embed_dims))
+            elif op == "ffn":
+                layers.append(AsymmetricFFN(2 * embed_dims, embed_dims, 4 * embed_dims))
+            elif op == "deformable":
+                layers.append(blocks.DeformableFeatureAggregation(
+                    embed_dims=embed_dims, num_groups=num_groups, num_levels=num_levels, num_cams=num_cams,
+                    attn_drop=0.15, use_camera_embed=True, residual_mode="cat", kps_generator=kps))
+            elif op == "qg_cross_attn":
+                layers.append(msda.QueryGroupMultiScaleDeformableAttention(
+                    embed_dims=embed_dims, num_heads=8, num_levels=num_levels, num_points=4, num_cams=num_cams,
+                    batch_first=True, residual_mode="cat"))
+            elif op == "refine3d":
+                layers.append(Refine3D(embed_dims))
+            elif op == "refine2d":
+                layers.append(Refine2D(embed_dims))
+            elif op == "allocation":
+                layers.append(DynamicQueryAllocation())
+            elif op == "aggregation":
+                layers.append(nn.ModuleDict(dict(reweight=ReWeight(), self_attn=mha())))
+            else:
+                raise NotImplementedError(op)
+        self.layers = nn.ModuleList(layers)
+        self.op_events = None
+        self.reset()
+
+    def reset(self):
+        self.cached_feature = self.cached_anchor = self.cached_conf = None
+        self.cached_T = self.cached_time = None
+
+    def group_mask(self, n, groups, like):
+        key = (n, tuple(groups), like.device)
+        if getattr(self, "_gmask_key", None) != key:
+            m = like.new_full((n, n), float("-inf"))
+            for a, b in groups:
+                m[a:b, a:b] = 0
+            self._gmask_key, self._gmask = key, m
+        return self._gmask
+
+    # simpb_head.py:300-322 (decouple_attn branch)
+    def graph(self, attn, query, key=None, value=None, query_pos=None, key_pos=None, two_d=False, mask=None,
+              key_padding_mask=None):
+        before, after = (self.fc_before2d, self.fc_after2d) if two_d else (self.fc_before, self.fc_after)
+        q = torch.cat([query, query_pos], dim=-1)
+        k = torch.cat([key, key_pos], dim=-1) if key is not None else q
+        v = before(value if value is not None else query)
+        out = attn(q, k, v, attn_mask=mask, key_padding_mask=key_padding_mask, need_weights=False)[0]
+        return after(q + out) if not two_d else after(q + torch.nan_to_num(out))
+
+    def forward(self, feature_maps, metas):
+        """feature_maps = [col_feats, spatial_shape, scale_start_index]; metas: projection_mat [bs,6,4,4],
+        image_wh [bs,6,2], and either timestamp [bs] + T_global [bs,4,4] (ego pose; the bank keeps the
+        previous frame's) or, precomputed by the caller, T_temp2cur [bs,4,4] + dt [bs] (static-shape /
+        CUDA-graph use; `img_wh` = (w, h) as Python floats then avoids the host sync of the allocation).
+        Returns the last layer's (anchor, classification, quality)."""
+        col, shape, start = feature_maps
+        bs = col.shape[0]
+        proj, wh = metas["projection_mat"], metas["image_wh"]
+        # ---- instance_bank.get (:79-119)
+        feature = self.instance_feature[None].expand(bs, -1, -1)
+        anchor = self.anchor[None].expand(bs, -1, -1)
+        temp_feature = temp_anchor = None
+        time_interval = col.new_full((bs,), 0.5)
+        if self.cached_anchor is not None and self.cached_anchor.shape[0] == bs:
+            if "T_temp2cur" in metas:
+                dt, T = metas["dt"].to(col.dtype), metas["T_temp2cur"]
+            else:
+                dt = (metas["timestamp"] - self.cached_time).to(col.dtype)
+                T = torch.linalg.inv(metas["T_global"]) @ self.cached_T      # previous ego frame -> current
+            temp_anchor = self.anchor_handler.anchor_projection(self.cached_anchor, [T.to(col.dtype)],
+                                                                time_intervals=[-dt])[0]
+            temp_feature = self.cached_feature
+            time_interval = torch.where(dt != 0, dt, time_interval)
+        anchor_embed = self.anchor_encoder(anchor)
+        temp_embed = self.anchor_encoder(temp_anchor) if temp_anchor is not None else None
+        # ---- prepare2d (:282-292): the 2-D branch gathers from the SAME table, viewed per camera
+        K = shape.shape[0]
+        value2d = col.reshape(bs * K, -1, self.embed_dims)
+        shapes2d, starts2d = shape[0], start[0]
+        n_pred = 0
+        temp_attn_instance = feature
+        cls = qt = None
+        marks = self.op_events           # optional [(op, start event, end event)] for the per-op breakdown
+        for i, op in enumerate(OPERATION_ORDER):
+            layer = self.layers[i]
+            if marks is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            if op == "norm" or op == "ffn":
+                feature = layer(feature)
+            elif op == "allocation":
+                ref2d, depth2d, trans, center, groups, valid2d = layer(anchor, proj, metas.get("img_wh", wh),
+                                                                       cap=self.static_queries)
+                feature = torch.matmul(trans, feature)                       # 3-D features -> 2-D queries
+                anchor2d = ref2d
+                embed2d = self.anchor_encoder2d(anchor2d)
+                gmask = self.group_mask(anchor2d.shape[1], groups, col)      # attention inside a camera only
+                pad2d = None if valid2d is None else ~valid2d
+            elif op == "qg_self_attn":
+                feature = self.graph(layer, feature, query_pos=embed2d, two_d=True, mask=gmask, key_padding_mask=pad2d)
+            elif op == "qg_cross_attn":
+                feature = layer(query=feature, query_pos=embed2d, reference_points=anchor2d.unsqueeze(2),
+                                value=value2d, spatial_shapes=shapes2d, level_start_index=starts2d,
+                                query_groups=groups)
+            elif op == "refine2d":
+                anchor2d, _, _ = layer(feature, anchor2d, embed2d)
+            elif op == "aggregation":
+                param = torch.cat([feature, center.sum(-1, keepdim=True)], dim=-1)
+                from2d, pos_from2d = layer["reweight"](feature, embed2d, param, trans)
+                feature = self.graph(layer["self_attn"], temp_attn_instance + from2d, query_pos=anchor_embed + pos_from2d)
+                anchor_embed = anchor_embed + pos_from2d
+            elif op == "gnn":
+                feature = self.graph(layer, feature, query_pos=anchor_embed)
+            elif op == "temp_gnn":
+                if temp_feature is not None:
+                    feature = self.graph(layer, feature, temp_feature, temp_feature, anchor_embed, temp_embed)
+                else:
+                    feature = self.graph(layer, feature, query_pos=anchor_embed)
+                temp_attn_instance = feature
+            elif op == "deformable":
+                feature = layer(feature, anchor, anchor_embed, feature_maps, metas)
+            elif op == "refine3d":
+                last = i == len(OPERATION_ORDER) - 1
+                anchor, c, q = layer(feature, anchor, anchor_embed, time_interval,
+                                     return_cls=last or n_pred == self.num_single_frame_decoder - 1)
+                cls, qt = (c, q) if c is not None else (cls, qt)
+                n_pred += 1
+                if n_pred == self.num_single_frame_decoder and temp_feature is not None:
+                    # instance_bank.update (:121-152): the best 300 new instances join the 600 temporal ones
+                    conf = c.max(dim=-1).values
+                    idx = conf.topk(self.num_anchor - self.num_temp, dim=1).indices
+                    pick = lambda t: torch.gather(t, 1, idx[..., None].expand(-1, -1, t.shape[-1]))   # noqa: E731
+                    feature = torch.cat([temp_feature, pick(feature)], dim=1)
+                    anchor = torch.cat([temp_anchor, pick(anchor)], dim=1)
+                if not last:
+                    anchor_embed = self.anchor_encoder(anchor)
+                if n_pred > self.num_single_frame_decoder and temp_embed is not None:
+                    temp_embed = anchor_embed[:, :self.num_temp]
+            if marks is not None:
+                ev[1].record()
+                marks.append((op, ev[0], ev[1]))
+        # ---- instance_bank.cache (:154-170)
+        conf = cls.max(dim=-1).values.sigmoid()
+        if self.cached_conf is not None:
+            conf = torch.cat([torch.maximum(self.cached_conf * self.confidence_decay, conf[:, :self.num_temp]),
+                              conf[:, self.num_temp:]], dim=1)
+        top_conf, idx = conf.topk(self.num_temp, dim=1)
+        pick = lambda t: torch.gather(t, 1, idx[..., None].expand(-1, -1, t.shape[-1]))               # noqa: E731
+        if self.cached_conf is not None and self.static_queries is not None:
+            # static buffers: a captured frame reads at its start what the previous replay wrote here
+            self.cached_conf.copy_(top_conf)
+            self.cached_feature.copy_(pick(feature))
+            self.cached_anchor.copy_(pick(anchor))
+        else:
+            self.cached_conf = top_conf
+            self.cached_feature, self.cached_anchor = pick(feature).detach(), pick(anchor).detach()
+        self.cached_T, self.cached_time = metas.get("T_global"), metas.get("timestamp")
+        return anchor, cls, qt
+
+
+class FPN(nn.Module):
+    """mmdet FPN as configured (config :93-100): 4 inputs [256, 512, 1024, 2048] -> 4 outputs of 256
+    channels (num_outs == number of inputs: no extra convolutions), nearest-neighbour top-down path."""
+
+    def __init__(self, in_channels=(256, 512, 1024, 2048), out_channels=256):
+        super().__init__()
+        self.lateral = nn.ModuleList(nn.Conv2d(c, out_channels, 1) for c in in_channels)
+        self.output = nn.ModuleList(nn.Conv2d(out_channels, out_channels, 3, padding=1) for _ in in_channels)
+
+    def forward(self, feats):
+        lat = [l(f) for l, f in zip(self.lateral, feats)]
+        for i in range(len(lat) - 1, 0, -1):
+            lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[-2:], mode="nearest")
+        return [o(x) for o, x in zip(self.output, lat)]
+
+
+class SimPBFrame(nn.Module):
+    """models/simpb.py:63-122 at inference: images [bs, 6, 3, 256, 704] -> ResNet-50 + FPN under fp16
+    autocast (auto_fp16, fp32 out) -> feature_maps_format -> head."""
+
+    def __init__(self, seed=0, static_queries=None):
+        super().__init__()
+        import torchvision
+        torch.manual_seed(seed)
+        r = torchvision.models.resnet50(weights=None)
+        self.stem = nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool)
+        self.stages = nn.ModuleList([r.layer1, r.layer2, r.layer3, r.layer4])
+        self.neck = FPN()
+        self.head = FrameDecoder(seed=seed, static_queries=static_queries)
+
+    def extract_feat(self, img):
+        bs, K = img.shape[:2]
+        with torch.autocast("cuda", dtype=torch.float16):
+            x = self.stem(img.flatten(0, 1).contiguous(memory_format=torch.channels_last))
+            feats = []
+            for s in self.stages:
+                x = s(x)
+                feats.append(x)
+            maps = self.neck(feats)
+        return feature_maps_format([m.float().reshape(bs, K, *m.shape[1:]) for m in maps])
+
+    def forward(self, img, metas):
+        return self.head(self.extract_feat(img), metas)

@@ -42,11 +42,20 @@ class _FlattenMaps(torch.autograd.Function):
         return (None,) + tuple(out)
 
 
+_TABLES = {}
+
+
 def _tables(sizes, num_cams, device):
-    shape = torch.tensor([list(sizes)] * num_cams, dtype=torch.int64, device=device)
-    counts = (shape[..., 0] * shape[..., 1]).flatten()
-    start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]]).reshape(num_cams, -1)
-    return shape, start
+    """The two small integer tables, built on the host once per (sizes, cameras, device) and cloned
+    per call: no host-to-device copy on later calls, so a warmed-up call can be graph-captured."""
+    key = (tuple(sizes), num_cams, str(device))
+    if key not in _TABLES:
+        shape = torch.tensor([list(sizes)] * num_cams, dtype=torch.int64)
+        counts = (shape[..., 0] * shape[..., 1]).flatten()
+        start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]]).reshape(num_cams, -1)
+        _TABLES[key] = (shape.to(device), start.to(device))
+    shape, start = _TABLES[key]
+    return shape.clone(), start.clone()
 
 
 def feature_maps_format(feature_maps, inverse=False, dtype=None, reference_start_index=False):

@@ -160,7 +160,7 @@ def test_r50_shape_rig_vs_oracle():
     check_case(synthetic.rig_op_inputs(bs=2, seed=3))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 30, 31, 32, 33])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 30, 31, 32, 33, 50, 51])
 def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
     """DFA_FWD_VARIANT selects the forward kernel family / tuning point; all of them must agree
     with the oracle (fp32 and bf16 feature tables, sparse rig and dense uniform locations)."""
@@ -179,6 +179,39 @@ def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
             ref = oracle.forward(g["feat"].float().cpu(), d["spatial_shape"], d["scale_start_index"],
                                  d["sampling_location"], d["weights"])
             assert_close(out, ref, RTOL_F32, "variant %d %s" % (variant, dtype))
+
+
+@pytest.mark.parametrize("m_target,u", [(1, 4), (3, 2), (8, 4), (8, 6), (31, 4)])
+def test_group_sliced_forward_blocks(m_target, u, monkeypatch):
+    """Group-sliced, anchor-pooled forward (DFA_FWD_VARIANT=50/51): a CTA = one channel group of a block of
+    M anchors, the block's taps dealt to the warps in equal ranges.  Every block size and both anchor
+    orders must agree with the oracle on NaN-prefilled outputs — anchors without a valid sample (zeros),
+    anchors cut by a range boundary (partial rows), dense inputs (several passes), blocks spanning batch
+    items, odd sizes without TMA — and repeat bit for bit."""
+    from simpb_b200 import cabi, synthetic
+    monkeypatch.setenv("DFA_FWD_GS_M", str(m_target))
+    monkeypatch.setenv("DFA_FWD_GS_U", str(u))
+    empty = synthetic.rig_op_inputs(bs=2, A=45, seed=61)
+    empty["sampling_location"][0, 3:9] = -0.25          # six anchors in a row without a valid sample
+    empty["sampling_location"][1, 44] = 1.5              # and the very last one
+    cases = [synthetic.rig_op_inputs(bs=1, A=900, seed=62), empty,
+             synthetic.op_inputs_uniform(bs=1, A=70, seed=63),
+             small_case(64, bs=3, A=11, P=13, K=6, sizes=SIZES3, C=256, G=8),
+             small_case(65, bs=1, A=5, P=3, K=3, sizes=SIZES3, C=256, G=8),      # odd P*K: no TMA
+             small_case(66, bs=2, A=7, P=5, K=3, sizes=SIZES3, C=32, G=2),
+             small_case(67, bs=1, A=9, P=4, K=2, sizes=SIZES3, C=64, G=8)]
+    for variant in ("50", "51"):
+        monkeypatch.setenv("DFA_FWD_VARIANT", variant)
+        for d in cases:
+            for dtype in (torch.float32, torch.bfloat16):
+                g = dev(d, dtype)
+                ref = oracle.forward(g["feat"].float().cpu(), d["spatial_shape"], d["scale_start_index"],
+                                     d["sampling_location"], d["weights"])
+                bs, A = d["sampling_location"].shape[:2]
+                junk = torch.full((bs, A, g["feat"].shape[2]), float("nan"), device="cuda")
+                out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=junk)
+                assert_close(out, ref, RTOL_F32, "gs variant %s M=%d U=%d %s" % (variant, m_target, u, dtype))
+                assert torch.equal(out, cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"]))
 
 
 @pytest.mark.parametrize("anchors", [900, 950, 889])

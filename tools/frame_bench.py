@@ -1,0 +1,136 @@
+"""BASELINE.json config #2: SimPB+ R50 704x256 full-frame inference, bs=1, random-init weights, synthetic
+6-camera images, on one B200.  Frames after the first carry 600 temporal instances, so the temporal
+branch (temp_gnn, instance-bank update) is live.  Prints one JSON object: frames/s, the split between
+backbone+neck, feature_maps_format and the 50-op decoder, and the decoder's per-op-type breakdown
+(CUDA events).  The frame runs EAGERLY, like the reference (its query allocation syncs with the host
+in every 2-D layer, models/allocation.py:32,:94, so it cannot be graph-captured as a whole).
+Two modes: "eager" as above (data-dependent 2-D query counts), and "graph": every camera owns a fixed
+number of 2-D query slots (static shapes, no host sync), so the WHOLE frame — backbone, neck, flatten and
+the 50 decoder ops — is one CUDA-graph replay; the six images are copied from pinned host memory inside
+the timed frame.
+    python tools/frame_bench.py [--frames 12] [--warmup 4] [--mode eager|graph|both]
+"""
+import argparse
+import collections
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from simpb_b200 import decoder, synthetic  # noqa: E402
+
+
+def frame_metas(i, proj, wh, device):
+    """Ego motion: 5 m/s forward (lidar +y), 0.5 s between frames (nuScenes key frames)."""
+    T = torch.eye(4, device=device)[None].clone()
+    T[0, 1, 3] = 2.5 * i
+    return dict(projection_mat=proj, image_wh=wh, timestamp=torch.tensor([0.5 * i], device=device), T_global=T)
+
+
+def run(frames=12, warmup=4, seed=0, breakdown=True):
+    dev = "cuda"
+    model = decoder.SimPBFrame(seed=seed).to(dev).eval()
+    proj, wh = synthetic.camera_rig(1)
+    proj, wh = proj.to(dev), wh.to(dev)
+    gen = torch.Generator().manual_seed(seed)
+    imgs = [torch.randn(1, 6, 3, 256, 704, generator=gen).to(dev) for _ in range(3)]
+    times, parts = [], collections.defaultdict(list)
+    ops = collections.defaultdict(list)
+    with torch.no_grad():
+        for i in range(warmup + frames):
+            metas = frame_metas(i, proj, wh, dev)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            timed = i >= warmup
+            model.head.op_events = [] if (timed and breakdown) else None
+            torch.cuda.synchronize()
+            e[0].record()
+            fm = model.extract_feat(imgs[i % 3])
+            e[1].record()
+            out = model.head(fm, metas)
+            e[2].record()
+            torch.cuda.synchronize()
+            if timed:
+                times.append(e[0].elapsed_time(e[2]))
+                parts["backbone_neck_flatten_ms"].append(e[0].elapsed_time(e[1]))
+                parts["decoder_ms"].append(e[1].elapsed_time(e[2]))
+                per = collections.defaultdict(float)
+                for op, a, b in (model.head.op_events or []):
+                    per[op] += a.elapsed_time(b)
+                for k, v in per.items():
+                    ops[k].append(v)
+    ms = statistics.median(times)
+    n2d = None
+    rec = {"workload": "SimPB+ R50 704x256 frame, bs=1: 6 images -> ResNet-50 + FPN (fp16 autocast) -> "
+                       "feature_maps_format -> 50-op decoder, 900 anchors (600 temporal), eager",
+           "frames_per_sec": 1e3 / ms, "ms_per_frame": ms, "frames_timed": frames, "warmup_frames": warmup,
+           "split_ms": {k: statistics.median(v) for k, v in parts.items()},
+           "decoder_ops_ms": {k: round(statistics.median(v), 4) for k, v in sorted(ops.items())},
+           "decoder_op_counts": dict(collections.Counter(decoder.OPERATION_ORDER)),
+           "data": "synthetic images, random-init weights (no checkpoint / dataset in this image)",
+           "note": "structure restated from models/simpb_head.py:323-747 + config :58-72; not numerically "
+                   "pinned to the reference head (it needs mmcv/mmdet); the two gathers are this repository's "
+                   "parity-tested DFA and MSDA modules"}
+    assert torch.isfinite(out[0]).all() and torch.isfinite(out[1]).all()
+    return rec
+
+
+def run_graph(frames=30, warmup=4, seed=0, cap=320):
+    """The whole frame as ONE CUDA graph (static 2-D query slots).  Per frame: H2D copy of the six images
+    from pinned memory + the ego-motion inputs, one graph replay, D2H of the classification scores."""
+    dev = "cuda"
+    model = decoder.SimPBFrame(seed=seed, static_queries=cap).to(dev).eval()
+    proj, wh = synthetic.camera_rig(1)
+    gen = torch.Generator().manual_seed(seed)
+    host_imgs = [torch.randn(1, 6, 3, 256, 704, generator=gen).pin_memory() for _ in range(3)]
+    img = torch.empty(1, 6, 3, 256, 704, device=dev)
+    T = torch.eye(4)[None].clone()
+    T[0, 1, 3] = -2.5                       # previous ego frame -> current: 2.5 m behind
+    metas = dict(projection_mat=proj.to(dev), image_wh=wh.to(dev), img_wh=(704.0, 256.0),
+                 T_temp2cur=T.to(dev), dt=torch.full((1,), 0.5, device=dev))
+    host_cls = torch.empty(1, 900, 10).pin_memory()
+    stream = torch.cuda.Stream()
+    with torch.no_grad(), torch.cuda.stream(stream):
+        for i in range(3):                  # eager warm-up: creates the bank's (static) cache buffers
+            img.copy_(host_imgs[i % 3], non_blocking=True)
+            out = model(img, metas)
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            out = model(img, metas)
+        times = []
+        for i in range(warmup + frames):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            stream.synchronize()
+            e0.record(stream)
+            img.copy_(host_imgs[i % 3], non_blocking=True)
+            g.replay()
+            host_cls.copy_(out[1], non_blocking=True)
+            e1.record(stream)
+            stream.synchronize()
+            if i >= warmup:
+                times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    assert torch.isfinite(host_cls).all()
+    return {"workload": "same frame as ONE CUDA-graph replay: %d static 2-D query slots per camera (%d queries), "
+                        "images copied from pinned host memory and class scores copied back inside the frame"
+                        % (cap, 6 * cap),
+            "frames_per_sec": 1e3 / ms, "ms_per_frame": ms, "frames_timed": frames, "warmup_frames": warmup,
+            "h2d_bytes_per_frame": img.numel() * 4, "d2h_bytes_per_frame": host_cls.numel() * 4}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--mode", default="both", choices=["eager", "graph", "both"])
+    ap.add_argument("--no-breakdown", action="store_true")
+    a = ap.parse_args()
+    rec = {}
+    if a.mode in ("eager", "both"):
+        rec["eager"] = run(a.frames, a.warmup, breakdown=not a.no_breakdown)
+    if a.mode in ("graph", "both"):
+        rec["graph"] = run_graph(max(a.frames, 30), a.warmup)
+    print(json.dumps(rec))
