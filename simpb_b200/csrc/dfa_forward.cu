@@ -766,10 +766,9 @@ int launch_fwd_win(const void *feat, const int *shape, const int *start, const f
 
 // Group-sliced, anchor-pooled kernel: the grid is a whole number of waves of resident CTAs; a block of
 // M anchors x G group CTAs.  DFA_FWD_GS_M = anchors per block the launcher aims at (default 8).
-template <typename T, int LPS, int U, bool TMA>
+template <typename T, int LPS, int U, bool TMA, int MINB>
 int launch_fwd_gs(const void *feat, const int *shape, const int *start, const float *loc, const float *w,
                   float *out, const Dims &d, int interleave, cudaStream_t st) {
-  constexpr int MINB = 6;
   auto kern = dfa_fwd_gs_kernel<T, LPS, U, TMA, MINB>;
   const long long total = static_cast<long long>(d.bs) * d.A;
   const int sms = device_sm_count();
@@ -847,16 +846,22 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
       const bool tma = tma_ok(d, loc, w);
       const int il = variant == 51 ? 1 : 0;
       const int u = DFA_KNOB("DFA_FWD_GS_U", 4);
-#define GS2(LPS, U)                                                                          \
-  (tma ? launch_fwd_gs<T, LPS, U, true>(feat, shape, start, loc, w, out, d, il, st)            \
-       : launch_fwd_gs<T, LPS, U, false>(feat, shape, start, loc, w, out, d, il, st))
-#define GS(LPS) (u == 2 ? GS2(LPS, 2) : u == 6 ? GS2(LPS, 6) : GS2(LPS, 4))
+      const int minb = DFA_KNOB("DFA_FWD_GS_MINB", 6);
+#define GS3(LPS, U, MINB)                                                                          \
+  (tma ? launch_fwd_gs<T, LPS, U, true, MINB>(feat, shape, start, loc, w, out, d, il, st)            \
+       : launch_fwd_gs<T, LPS, U, false, MINB>(feat, shape, start, loc, w, out, d, il, st))
+#define GS2(LPS, U) GS3(LPS, U, 6)
+#define GS(LPS)                                                                                    \
+  (minb == 5 ? (u == 6 ? GS3(LPS, 6, 5) : GS3(LPS, 4, 5))                                          \
+             : minb == 4 ? (u == 8 ? GS3(LPS, 8, 4) : GS3(LPS, 6, 4))                              \
+                         : (u == 2 ? GS3(LPS, 2, 6) : u == 3 ? GS3(LPS, 3, 6) : GS3(LPS, 4, 6)))
       switch (lps) {
         case 8: return GS(8);
         case 4: return GS(4);
         case 2: return GS2(2, 4);
         default: return GS2(1, 4);
       }
+#undef GS3
 #undef GS
 #undef GS2
     }

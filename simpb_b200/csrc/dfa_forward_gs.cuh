@@ -34,11 +34,11 @@
 namespace {
 
 constexpr int GS_NT = 256;      // threads per CTA
-constexpr int GS_CAP = 768;     // tap records per pass (32 bytes each)
+constexpr int GS_CAP = 672;     // tap records per pass (32 bytes each): 6 CTAs per SM inside 196 KB of shared memory
 constexpr int GS_MMAX = 32;     // anchors per block the kernel supports (prefix sum by one warp)
 
 struct GsLayout {
-  uint32_t loc, list, nv, base, tab, rec, part, pj, bar, total, list_stride;
+  uint32_t loc, list, nv, base, tab, rec, part, pj, seg, bar, total, list_stride;
 };
 __host__ __device__ inline GsLayout gs_layout(int P, int K, int L, int mmax, int cpg) {
   GsLayout s;
@@ -53,6 +53,7 @@ __host__ __device__ inline GsLayout gs_layout(int P, int K, int L, int mmax, int
   s.tab = o, o = align_up(o + 12u * K * L, 16);
   s.part = o, o = align_up(o + 4u * (GS_NT / 32) * 2u * cpg, 16);
   s.pj = o, o = align_up(o + 4u * (GS_NT / 32) * 2u, 16);
+  s.seg = o, o = align_up(o + 16u * (GS_NT / 32) * (mmax < GS_MMAX ? mmax : GS_MMAX), 16);
   s.bar = o, o += 16;
   s.total = o;
   return s;
@@ -68,7 +69,6 @@ __global__ void __launch_bounds__(GS_NT, MINB)
   constexpr int VEC = FeatVec<T>::VEC;
   constexpr int TPI = 32 / (4 * LPS);  // taps per warp instruction
   constexpr int NW = GS_NT / 32;
-  constexpr int ITER = GS_CAP / GS_NT;
   extern __shared__ __align__(128) unsigned char smem[];
   const int cpg = d.C / d.G;
   const GsLayout lay = gs_layout(d.P, d.K, d.L, mmax, cpg);
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(GS_NT, MINB)
   int *s_tab = reinterpret_cast<int *>(smem + lay.tab);
   float *s_part = reinterpret_cast<float *>(smem + lay.part);
   int *s_pj = reinterpret_cast<int *>(smem + lay.pj);
+  int4 *s_seg = reinterpret_cast<int4 *>(smem + lay.seg);  // [warp][segment] = (first tap, end, destination, -)
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem + lay.bar);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -96,6 +97,8 @@ __global__ void __launch_bounds__(GS_NT, MINB)
     M = static_cast<int>(total * (blk + 1) / nblocks - a0);
   }
   const int PK = d.P * d.K;
+  DFA_STAMP(0);
+  DFA_GSTAMP(6);
 
   if (TMA) {
     if (tid == 0) {
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(GS_NT, MINB)
     if (lane == 0) s_nv[j] = n;
   }
   __syncthreads();
-  if (warp == 0) {  // exclusive prefix sum of the anchors' tap counts (M <= 32)
+  {  // exclusive prefix sum of the anchors' tap counts (M <= 32); every warp computes and stores the same values
     const int nt = lane < M ? s_nv[lane] * d.L : 0;
     int inc = nt;
 #pragma unroll
@@ -148,14 +151,14 @@ __global__ void __launch_bounds__(GS_NT, MINB)
     }
     if (lane < M) s_base[lane] = inc - nt;
     if (lane == M - 1) s_base[M] = inc;
+    __syncwarp();
   }
-  __syncthreads();
+  DFA_STAMP(1);
 
   const uint32_t rb16 = static_cast<uint32_t>(d.C) * sizeof(T) / 16u;  // row size in 16-byte units
   const int q = (lane / LPS) & 3, v = lane % LPS, sub = lane / (4 * LPS);
   const unsigned char *fb = reinterpret_cast<const unsigned char *>(feat) +
                             (static_cast<size_t>(grp) * cpg * sizeof(T) + 16u * v);
-  float *outg = out + grp * cpg + v * VEC;
 
   for (int j0 = 0; j0 < M;) {
     // pass = the longest run of whole anchors whose taps fit the record buffer
@@ -164,110 +167,140 @@ __global__ void __launch_bounds__(GS_NT, MINB)
     while (j1 < M && s_base[j1 + 1] - tb <= GS_CAP) ++j1;
     const int T_pass = s_base[j1] - tb;
 
-    // ---- records: one thread per tap.  Weight loads first, geometry while they are in flight.
-    float wv[ITER];
-    int meta[ITER];  // (j << 20) | (l << 16) | sample
+    // ---- records: one thread per valid (anchor, sample); its L taps sit at l * nv + i (level-major:
+    // coarse-level neighbours back to back).  Weight loads first, geometry while they are in flight.
+    const int NS = T_pass / d.L;
+    for (int i0 = tid; i0 < NS; i0 += GS_NT) {
+      int j = j0;
+      while ((s_base[j + 1] - tb) <= i0 * d.L) ++j;
+      const int nv = s_nv[j];
+      const int i = i0 - (s_base[j] - tb) / d.L;
+      const int s = s_list[j * lay.list_stride + i];
+      const long long an = a0 + static_cast<long long>(j) * astep;
+      const float *wp = weights + (an * PK + s) * d.L * d.G + grp;
+      const uint32_t item16 = static_cast<uint32_t>(an / d.A) * static_cast<uint32_t>(d.num_feat) * rb16;
+      const float x = s_loc[(j * PK + s) * 2], y = s_loc[(j * PK + s) * 2 + 1];
+      const int kl0 = (s % d.K) * d.L;
+      uint4 *rec = reinterpret_cast<uint4 *>(s_rec + 4 * ((s_base[j] - tb) + i));
+      for (int l0 = 0; l0 < d.L; l0 += 4) {
+        float wv[4];
 #pragma unroll
-    for (int it = 0; it < ITER; ++it) {
-      const int t = tid + it * GS_NT;
-      wv[it] = 0.f, meta[it] = -1;
-      if (t < T_pass) {
-        int j = j0;
-        while (s_base[j + 1] - tb <= t) ++j;
-        const int nv = s_nv[j];
-        const int local = t - (s_base[j] - tb);
-        const int l = local / nv, i = local - l * nv;  // level-major: coarse-level neighbours back to back
-        const int s = s_list[j * lay.list_stride + i];
-        const long long an = a0 + static_cast<long long>(j) * astep;
-        wv[it] = __ldg(weights + ((an * PK + s) * d.L + l) * d.G + grp);
-        meta[it] = (j << 20) | (l << 16) | s;
-      }
-    }
+        for (int u = 0; u < 4; ++u) wv[u] = l0 + u < d.L ? __ldg(wp + (l0 + u) * d.G) : 0.f;
 #pragma unroll
-    for (int it = 0; it < ITER; ++it) {
-      const int t = tid + it * GS_NT;
-      if (meta[it] >= 0) {
-        const int j = meta[it] >> 20, l = (meta[it] >> 16) & 15, s = meta[it] & 0xffff;
-        const long long an = a0 + static_cast<long long>(j) * astep;
-        const uint32_t item16 = static_cast<uint32_t>(an / d.A) * static_cast<uint32_t>(d.num_feat) * rb16;
-        const int kl = (s % d.K) * d.L + l;
-        TapGeom gm;
-        tap_geometry(s_loc[(j * PK + s) * 2], s_loc[(j * PK + s) * 2 + 1], s_tab[3 * kl], s_tab[3 * kl + 1],
-                     s_tab[3 * kl + 2], gm);
-        // a corner outside the map (zero padding) is redirected to an in-map corner of the same tap
-        // with coefficient 0 — a valid sample always has one — so the gather needs no predicates
-        const int safe = gm.row[0] >= 0 ? gm.row[0] : gm.row[1] >= 0 ? gm.row[1]
-                       : gm.row[2] >= 0 ? gm.row[2] : gm.row[3];
-        const float w = wv[it];
-        const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
-        uint32_t o[4];
-        float c[4];
+        for (int u = 0; u < 4; ++u) {
+          const int l = l0 + u;
+          if (l < d.L) {
+            TapGeom gm;
+            tap_geometry(x, y, s_tab[3 * (kl0 + l)], s_tab[3 * (kl0 + l) + 1], s_tab[3 * (kl0 + l) + 2], gm);
+            // a corner outside the map (zero padding) is redirected to an in-map corner of the same tap
+            // with coefficient 0 — a valid sample always has one — so the gather needs no predicates
+            const int safe = gm.row[0] >= 0 ? gm.row[0] : gm.row[1] >= 0 ? gm.row[1]
+                           : gm.row[2] >= 0 ? gm.row[2] : gm.row[3];
+            const float bw[4] = {gm.hh * gm.hw, gm.hh * gm.lw, gm.lh * gm.hw, gm.lh * gm.lw};
+            uint32_t o[4];
+            float c[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          o[k] = item16 + static_cast<uint32_t>(gm.row[k] >= 0 ? gm.row[k] : safe) * rb16;
-          c[k] = gm.row[k] >= 0 ? bw[k] * w : 0.f;
-        }
-        uint4 *dst = reinterpret_cast<uint4 *>(s_rec + 4 * t);
-        dst[0] = make_uint4(o[0], __float_as_uint(c[0]), o[1], __float_as_uint(c[1]));
-        dst[1] = make_uint4(o[2], __float_as_uint(c[2]), o[3], __float_as_uint(c[3]));
-      }
-    }
-    if (tid < 2 * NW) s_pj[tid] = -1;
-    __syncthreads();
-
-    // ---- gather: warp w owns taps [lo, hi) of the pass
-    int per = (T_pass + NW - 1) / NW;
-    per = (per + U * TPI - 1) / (U * TPI) * (U * TPI);
-    const int lo = min(warp * per, T_pass), hi = min(lo + per, T_pass);
-    int jj = j0;
-    while (jj + 1 < j1 && s_base[jj + 1] - tb <= lo) ++jj;
-    int slot = 0;
-    for (int t0 = lo; t0 < hi; ++jj) {
-      const int ab = s_base[jj] - tb, ae = s_base[jj + 1] - tb;  // this anchor's taps
-      const int se = min(ae, hi);
-      if (se <= t0) continue;  // anchor without taps
-      float acc[VEC];
-#pragma unroll
-      for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-      for (int t = t0; t < se; t += U * TPI) {
-        typename FeatVec<T>::raw_t val[U];
-        float cf[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int tt = t + u * TPI + sub;
-          if (tt < se) {
-            const uint2 rc = s_rec[4 * tt + q];
-            val[u] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + static_cast<size_t>(rc.x) * 16u));
-            cf[u] = __uint_as_float(rc.y);
-          } else {
-            val[u] = FeatVec<T>::zero_raw();
-            cf[u] = 0.f;
+            for (int k = 0; k < 4; ++k) {
+              o[k] = item16 + static_cast<uint32_t>(gm.row[k] >= 0 ? gm.row[k] : safe) * rb16;
+              c[k] = gm.row[k] >= 0 ? bw[k] * wv[u] : 0.f;
+            }
+            uint4 *dst = rec + 2 * l * nv;
+            dst[0] = make_uint4(o[0], __float_as_uint(c[0]), o[1], __float_as_uint(c[1]));
+            dst[1] = make_uint4(o[2], __float_as_uint(c[2]), o[3], __float_as_uint(c[3]));
           }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) FeatVec<T>::fma(acc, cf[u], val[u]);
       }
-      // fold corners (and sub-taps): lanes that hold the same vector of the slice
-#pragma unroll
-      for (int m = LPS; m < 32; m <<= 1)
-#pragma unroll
-        for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], m);
-      const bool whole = t0 == ab && se == ae;
-      if (lane < LPS) {
-        float4 *dst;
-        if (whole) {
-          dst = reinterpret_cast<float4 *>(outg + (a0 + static_cast<long long>(jj) * astep) * d.C);
-        } else {
-          dst = reinterpret_cast<float4 *>(s_part + (warp * 2 + slot) * cpg + v * VEC);
-          if (lane == 0) s_pj[warp * 2 + slot] = jj;
-        }
-#pragma unroll
-        for (int c = 0; c < VEC / 4; ++c)
-          dst[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
-      }
-      if (!whole) slot = 1;  // a range has at most two cut anchors: its first and its last
-      t0 = se;
     }
+    DFA_STAMP(2);
+    if (lane < 2) s_pj[warp * 2 + lane] = -1;  // this warp's two partial-row slots: unused
+    __syncwarp();
+    // ---- the warp's share of the pass: taps [lo, hi), cut into one segment per anchor it meets.
+    // lane i looks at anchor j0 + i (a pass has at most 32 anchors).
+    int nseg;
+    {
+      int per = (T_pass + NW - 1) / NW;
+      per = (per + U * TPI - 1) / (U * TPI) * (U * TPI);
+      const int lo = min(warp * per, T_pass), hi = min(lo + per, T_pass);
+      const int j = j0 + lane;
+      int sb = 0, se = 0, ab = 0, ae = 0;
+      if (j < j1) {
+        ab = s_base[j] - tb, ae = s_base[j + 1] - tb;
+        sb = max(ab, lo), se = min(ae, hi);
+      }
+      const bool live = se > sb, cut = live && (sb != ab || se != ae);
+      const unsigned mlive = __ballot_sync(0xffffffffu, live), mcut = __ballot_sync(0xffffffffu, cut);
+      const unsigned below = (1u << lane) - 1u;
+      if (live) {
+        // destination: the output row itself (float index), or partial-row slot 0 / 1 of this warp
+        // (a range cuts at most two anchors: its first and its last)
+        int dst;
+        if (cut) {
+          const int slot = __popc(mcut & below);
+          dst = -1 - slot;
+          s_pj[warp * 2 + slot] = j;
+        } else {
+          dst = static_cast<int>((a0 + static_cast<long long>(j) * astep) * d.C);
+        }
+        s_seg[warp * mmax + __popc(mlive & below)] = make_int4(sb, se, dst, 0);
+      }
+      nseg = __popc(mlive);
+    }
+    __syncthreads();
+    DFA_STAMP(3);
+
+    // ---- gather
+    {
+      const unsigned char *recl = reinterpret_cast<const unsigned char *>(s_rec) + 8 * q + 32 * sub;
+#pragma unroll 1
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int4 sd = s_seg[warp * mmax + sg];
+        const int se = sd.y;
+        float acc[VEC];
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+        // full batches: U warp instructions = U * TPI taps, all loads issued before the first use
+        int t = sd.x;
+#pragma unroll 1
+        for (; t + U * TPI <= se; t += U * TPI) {
+          typename FeatVec<T>::raw_t val[U];
+          float cf[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint2 rc = *reinterpret_cast<const uint2 *>(recl + 32 * (t + u * TPI));
+            val[u] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + static_cast<size_t>(rc.x) * 16u));
+            cf[u] = __uint_as_float(rc.y);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) FeatVec<T>::fma(acc, cf[u], val[u]);
+        }
+        if (t < se) {  // last, partial batch: slots past the end replay the segment's last tap with coefficient 0
+          typename FeatVec<T>::raw_t val[U];
+          float cf[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int tt = t + u * TPI + sub;
+            const uint2 rc = s_rec[4 * min(tt, se - 1) + q];
+            val[u] = FeatVec<T>::load_raw(reinterpret_cast<const T *>(fb + static_cast<size_t>(rc.x) * 16u));
+            cf[u] = tt < se ? __uint_as_float(rc.y) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) FeatVec<T>::fma(acc, cf[u], val[u]);
+        }
+        // fold corners (and sub-taps): lanes that hold the same vector of the slice
+#pragma unroll
+        for (int m = LPS; m < 32; m <<= 1)
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], m);
+        if (lane < LPS) {
+          float4 *dst = sd.z >= 0 ? reinterpret_cast<float4 *>(out + sd.z + grp * cpg + lane * VEC)
+                                  : reinterpret_cast<float4 *>(s_part + (warp * 2 + (-1 - sd.z)) * cpg + lane * VEC);
+#pragma unroll
+          for (int c = 0; c < VEC / 4; ++c)
+            dst[c] = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        }
+      }
+    }
+    DFA_STAMP(4);
     __syncthreads();
 
     // ---- anchors cut by a range boundary: sum the partial rows in warp order; anchors without a
@@ -285,6 +318,8 @@ __global__ void __launch_bounds__(GS_NT, MINB)
     j0 = j1;
     if (j0 < M) __syncthreads();  // records and partial rows are rewritten by the next pass
   }
+  DFA_STAMP(5);
+  DFA_GSTAMP(7);
 }
 
 // Shape test: a group slice is 1, 2, 4 or 8 16-byte vectors, rows and the table are 16-byte aligned,
@@ -299,6 +334,7 @@ int gs_lps(const Dims &d, const void *feat, const float *out) {
     return 0;
   if (static_cast<long long>(d.bs) * d.num_feat * d.C * static_cast<long long>(sizeof(T)) >= (1ll << 36)) return 0;
   if (((d.C / d.G) * 4) % 16 != 0) return 0;  // float4 stores of an output slice
+  if (static_cast<long long>(d.bs) * d.A * d.C >= (1ll << 31)) return 0;  // 32-bit output index in the segment records
   return static_cast<int>(lps);
 }
 

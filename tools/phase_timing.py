@@ -19,13 +19,17 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--variant", type=int, default=10)
 ap.add_argument("--nw", type=int, default=4)
 ap.add_argument("--inputs", default="rig")
+ap.add_argument("--build-only", action="store_true")
 a = ap.parse_args()
 os.environ["DFA_FWD_VARIANT"] = str(a.variant)
-lib_path = os.path.join(ROOT, "gpurun_out", "libdfa_b200_prof.so")
-os.makedirs(os.path.dirname(lib_path), exist_ok=True)
-objs, _ = build.compile_objects(extra_flags=["-DDFA_PHASE_TIMING"],
-                                obj_dir=os.path.join(ROOT, "gpurun_out", "prof_objs"))
-build.link_lib(objs, lib_path)
+prof_dir = os.path.join(ROOT, "tools", "_prof")          # git-ignored; travels with the snapshot, so build it
+lib_path = os.path.join(prof_dir, "libdfa_b200_prof.so")   # in the container (python tools/phase_timing.py --build-only)
+os.makedirs(prof_dir, exist_ok=True)
+if build._stale(lib_path, build.KERNEL_SRCS + build.HEADERS + [build.HEADER]):
+    objs, _ = build.compile_objects(extra_flags=["-DDFA_PHASE_TIMING"], obj_dir=os.path.join(prof_dir, "objs"))
+    build.link_lib(objs, lib_path)
+if a.build_only:
+    sys.exit(0)
 lib = ctypes.CDLL(lib_path)
 
 
@@ -58,7 +62,10 @@ torch.cuda.synchronize()
 t = buf.cpu().double()
 t = t[t[:, 0, 0] > 0]       # CTAs that ran
 rows_like = a.variant < 10 or a.variant >= 30
-if a.variant >= 40:    # channel-sliced kernel
+if a.variant >= 50:    # group-sliced, anchor-pooled kernel
+    names = ["0 start", "1 locations landed, compaction, prefix", "2 records built", "3 segments + barrier",
+             "4 gather done", "5 end", "-", "-"]
+elif a.variant >= 40:    # channel-sliced kernel
     names = ["0 start", "1 locations landed, camera masks", "2 barrier + plan (+ weights landed)", "3 fine rows built, barrier",
              "4 gather done", "5 end", "-", "-"]
 elif a.variant >= 30:    # window-merging kernel
