@@ -450,9 +450,11 @@ def run_own_arm(args):
                 "roofline": roof}
 
     # ---- end to end through the host-buffer C ABI entry point (every rank; the slowest rank counts)
-    def e2e_leg(dt):
+    def e2e_leg(dt, pull=True):
         d0 = host[0]
         dims = cabi.Dims(args.batch, 6, d0["num_feat"], 256, 4, args.anchors, 13, 8)
+        os.environ["DFA_HOST_PULL"] = "1" if pull else "0"
+        cabi.reload_knobs()
         hf = cabi.HostForward(dims, dt)
         pin = lambda x: x.contiguous().pin_memory()  # noqa: E731
         h = [dict(feat=pin(d["mc_ms_feat"].to(dt)), shape=pin(d["spatial_shape"].int()),
@@ -468,26 +470,36 @@ def run_own_arm(args):
             x = h[i % 2]
             hf(x["feat"], x["shape"], x["start"], x["loc"], x["w"], h_out)   # ends with a stream sync
         ms = 1e3 * (time.perf_counter() - t0) / n
-        h2d = sum(h[0][k].numel() * h[0][k].element_size() for k in ("feat", "shape", "start", "loc", "w"))
+        h2d, rows, wbytes = hf.stats()      # what the last call moved host -> device (counted on the device)
+        whole = sum(h[0][k].numel() * h[0][k].element_size() for k in ("feat", "shape", "start", "loc", "w"))
         per_rank = gather_ranks(ms)
         del hf, h
+        os.environ.pop("DFA_HOST_PULL", None)
+        cabi.reload_knobs()
         return {"ms_per_step": max(per_rank), "per_rank_ms": per_rank, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": h_out.numel() * 4, "steps": n,
+                "host_operand_bytes": whole, "feature_rows_moved": rows, "weight_bytes_moved": wbytes,
                 "h2d_GBps_per_rank": [h2d / (m * 1e-3) / 1e9 for m in per_rank],
                 "h2d_GBps_all_ranks": sum(h2d / (m * 1e-3) / 1e9 for m in per_rank)}
 
     e = e2e_leg(dtype)
+    e_copy = e2e_leg(dtype, pull=False)
     e_bf16 = e2e_leg(torch.bfloat16) if dtype != torch.bfloat16 else None
     if rank == 0:
         line["e2e"] = {"value": queries / (e["ms_per_step"] / 1e3), "unit": UNIT,
-                       "api": "dfa_forward_host (C ABI, pinned host buffers)", **e,
-                       "limiter": "the host link: one PCIe Gen5 x16 per GPU (~55 GB/s achieved); with several "
-                                  "ranks also the host's memory / root-complex bandwidth (h2d_GBps_all_ranks)",
-                       "cpu_affinity_cores": len(os.sched_getaffinity(0))}
+                       "api": "dfa_forward_host (C ABI, pinned host buffers; pull mode: the device reads the "
+                              "feature rows and weight lines the forward references straight from the pinned "
+                              "host buffers, everything else is copied whole; include/dfa_b200.h)", **e,
+                       "limiter": "the host link: one PCIe Gen5 x16 per GPU; with several ranks also the host's "
+                                  "memory / root-complex bandwidth (h2d_GBps_all_ranks)",
+                       "cpu_affinity_cores": len(os.sched_getaffinity(0)),
+                       "whole_copy": {"value": queries / (e_copy["ms_per_step"] / 1e3), "unit": UNIT, **e_copy,
+                                      "note": "same call with DFA_HOST_PULL=0: all five inputs copied whole "
+                                              "(the only mode of round 1)"}}
         if e_bf16 is not None:
             line["e2e"]["bf16_table"] = {"value": queries / (e_bf16["ms_per_step"] / 1e3), "unit": UNIT, **e_bf16,
                                          "note": "same call with a bfloat16 feature table on the host: "
-                                                 "half the bytes over the link"}
+                                                 "half the feature bytes over the link"}
 
     # ---- the training configuration on every rank (BASELINE.json config #3)
     if not args.no_extras and args.workload == "fwd":
@@ -651,6 +663,16 @@ def extras(args, cabi, host, peak, roof):
     except Exception as e:  # pragma: no cover
         other["error"] = repr(e)
     roof["other_shapes"] = other
+    # ---- BASELINE.json config #2: the SimPB+ R50 frame (frames/s), tools/frame_bench.py
+    try:
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import frame_bench
+        fr = frame_bench.run(frames=8, warmup=3)
+        fr["whole_frame_cuda_graph"] = frame_bench.run_graph(frames=30, warmup=4)
+        roof["frame"] = fr
+    except Exception as e:  # pragma: no cover
+        roof["frame"] = {"error": repr(e)}
 
 
 def main():

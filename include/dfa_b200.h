@@ -196,15 +196,27 @@ int dfa_msda_backward(const void *value, int value_dtype, const int32_t *spatial
                       int num_heads, int head_dim, int num_query, int num_levels, int num_points,
                       int num_tables, const int32_t *query_table, int zero_grad_value, void *stream);
 
-/* Forward with HOST buffers: host→device copies of all five inputs, the kernel, and the
- * device→host copy of the output, on `stream`, then a stream synchronise.  Host buffers should
- * be pinned for the copies to be asynchronous.  `workspace` is a device buffer of at least
- * dfa_forward_host_workspace_bytes() bytes (the library never allocates). */
+/* Forward with HOST buffers: the inputs go host→device, the kernel runs, the output comes back
+ * device→host, all on `stream`, then a stream synchronise.  `workspace` is a device buffer of at least
+ * dfa_forward_host_workspace_bytes() bytes (the library never allocates).
+ *
+ * How the inputs travel depends on the host buffers:
+ *   - pinned AND mapped (cudaHostAlloc / cudaHostRegister(…Mapped): device-accessible): PULL mode.  The
+ *     small operands are copied whole; the device then marks the feature rows the forward will read
+ *     (the op's own validity test and corner geometry, so the set is exact) and reads exactly those
+ *     rows — and the weight lines of the valid samples — straight from host memory.  With camera-rig
+ *     inputs that is about a quarter of the table.  The output is bit-identical to the whole-copy path.
+ *   - anything else (pageable, or DFA_HOST_PULL=0): whole copies of all five inputs; pinned buffers
+ *     make them asynchronous.
+ * dfa_forward_host_stats() reports what the LAST call on this workspace moved host→device: total
+ * bytes, feature rows and weight bytes (whole-copy mode: everything). */
 int64_t dfa_forward_host_workspace_bytes(int feat_dtype, const dfa_dims *dims);
 int dfa_forward_host(const void *h_mc_ms_feat, int feat_dtype, const int32_t *h_spatial_shape,
                      const int32_t *h_scale_start_index, const float *h_sampling_location,
                      const float *h_weights, float *h_output, const dfa_dims *dims,
                      void *workspace, int64_t workspace_bytes, void *stream);
+int dfa_forward_host_stats(const void *workspace, int feat_dtype, const dfa_dims *dims, void *stream,
+                           int64_t *h2d_bytes, int64_t *rows_moved, int64_t *weight_bytes_moved);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ LIB = os.path.join(PKG, "libdfa_b200.so")
 KERNEL_SRCS = [os.path.join(PKG, "csrc", n) for n in ("dfa_forward.cu", "dfa_backward.cu", "dfa_frontend.cu",
                                                         "dfa_msda.cu")]
 COMMON_HDR = os.path.join(PKG, "csrc", "dfa_common.cuh")
-HEADERS = [os.path.join(PKG, "csrc", n) for n in ("dfa_common.cuh", "dfa_forward_win.cuh", "dfa_forward_gs.cuh")]
+HEADERS = [os.path.join(PKG, "csrc", n) for n in ("dfa_common.cuh", "dfa_forward_win.cuh")]
 OBJ_DIR = os.path.join(PKG, "csrc", "build")
 EXT_SRC = os.path.join(PKG, "csrc", "dfa_torch_ext.cpp")
 HEADER = os.path.join(ROOT, "include", "dfa_b200.h")

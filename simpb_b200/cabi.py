@@ -22,7 +22,7 @@ SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_debug_reload_knobs", "dfa_for
            "dfa_softmax_weights", "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
            "dfa_softmax_weights_split_backward",
            "dfa_msda_forward", "dfa_msda_backward",
-           "dfa_forward_host_workspace_bytes", "dfa_forward_host")
+           "dfa_forward_host_workspace_bytes", "dfa_forward_host", "dfa_forward_host_stats")
 
 
 class DfaError(RuntimeError):
@@ -68,11 +68,12 @@ def _load():
     lib.dfa_forward_host_workspace_bytes.restype = i64
     lib.dfa_forward_host_workspace_bytes.argtypes = [i32, dp]
     lib.dfa_forward_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp, i64, vp]
+    lib.dfa_forward_host_stats.argtypes = [vp, i32, dp, vp, vp, vp, vp]
     for name in ("dfa_forward", "dfa_backward", "dfa_debug_indices", "dfa_flatten_maps",
                  "dfa_keypoints_project", "dfa_keypoints_project_backward", "dfa_softmax_weights",
                  "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
                  "dfa_softmax_weights_split_backward", "dfa_msda_forward", "dfa_msda_backward",
-                 "dfa_forward_host"):
+                 "dfa_forward_host", "dfa_forward_host_stats"):
         getattr(lib, name).restype = i32
     return lib
 
@@ -476,8 +477,10 @@ def msda_backward(value, shapes, start, loc, w, grad_out, need_value=True, query
 
 
 class HostForward:
-    """End-to-end forward with HOST (pinned) buffers through dfa_forward_host: host→device copies,
-    the kernel and the device→host copy of the result all happen inside the call."""
+    """End-to-end forward with HOST buffers through dfa_forward_host: the inputs' trip to the device,
+    the kernel and the device→host copy of the result all happen inside the call.  Pinned (mapped)
+    host tensors take the pull mode — only the rows and weight lines the forward reads cross the link;
+    pageable ones are copied whole (include/dfa_b200.h).  stats() = what the last call moved."""
 
     def __init__(self, dims, dtype=torch.float32, device="cuda"):
         self.dims = dims
@@ -502,3 +505,12 @@ class HostForward:
                                        self.workspace.data_ptr(), self.nbytes,
                                        stream_ptr(self.device)), "dfa_forward_host")
         return h_out
+
+    def stats(self):
+        """(host→device bytes, feature rows, weight bytes) moved by the last call."""
+        v = [ctypes.c_int64(0) for _ in range(3)]
+        with torch.cuda.device(self.device):
+            check(lib.dfa_forward_host_stats(self.workspace.data_ptr(), self.dt, ctypes.byref(self.dims),
+                                             stream_ptr(self.device), ctypes.byref(v[0]), ctypes.byref(v[1]),
+                                             ctypes.byref(v[2])), "dfa_forward_host_stats")
+        return tuple(int(x.value) for x in v)

@@ -636,10 +636,96 @@ __global__ void dfa_debug_indices_kernel(const int *__restrict__ shape, const in
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// dfa_forward_host, pull mode: only what the forward will read crosses the host link
+// ------------------------------------------------------------------------------------------
+// With camera-rig inputs ~19 % of the samples are valid and ~27 % of the feature rows are referenced at
+// all.  When the host buffers are pinned and mapped (device-accessible), the device marks the rows the
+// forward will touch — same sample_valid / tap_geometry as every kernel, so the set is exact — and
+// pulls exactly those rows, and the weight lines of the valid samples, straight from host memory.
+// Workspace header: [0] rows pulled, [1] 16-byte weight vectors pulled, [2] bytes per row, [3] bytes of
+// the small operands copied whole.
+__global__ void dfa_host_mark_kernel(const int *__restrict__ shape, const int *__restrict__ start,
+                                     const float *__restrict__ loc, uint32_t *__restrict__ bitmap,
+                                     uint8_t *__restrict__ svalid, unsigned long long *__restrict__ hdr,
+                                     unsigned long long row_bytes, unsigned long long fixed_bytes, Dims d) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) hdr[2] = row_bytes, hdr[3] = fixed_bytes;
+  const long long n = static_cast<long long>(d.bs) * d.A * d.P * d.K;
+  const long long per_item = static_cast<long long>(d.A) * d.P * d.K;
+  for (long long s = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; s < n;
+       s += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(s % d.K);
+    const long long row0 = (s / per_item) * d.num_feat;
+    const float x = loc[2 * s], y = loc[2 * s + 1];
+    const bool ok = sample_valid(x, y);
+    svalid[s] = ok ? 1 : 0;
+    if (!ok) continue;
+    for (int l = 0; l < d.L; ++l) {
+      const int kl = k * d.L + l;
+      TapGeom gm;
+      tap_geometry(x, y, __ldg(shape + 2 * kl), __ldg(shape + 2 * kl + 1), __ldg(start + kl), gm);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (gm.row[q] >= 0) {
+          const long long r = row0 + gm.row[q];
+          atomicOr(bitmap + (r >> 5), 1u << (r & 31));
+        }
+    }
+  }
+}
+
+// One warp per bitmap word (32 rows); up to four marked rows are copied at a time so that a lane keeps
+// several 16-byte host reads in flight.  `src` is the device alias of the pinned host table.
+__global__ void dfa_host_pull_rows_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                          const uint32_t *__restrict__ bitmap, long long nwords,
+                                          long long nrows, int row_vecs, unsigned long long *__restrict__ hdr) {
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  unsigned long long pulled = 0;
+  for (long long w = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); w < nwords;
+       w += nwarps) {
+    uint32_t m = bitmap[w];
+    if (w * 32 + 32 > nrows) m &= (1u << (nrows - w * 32)) - 1u;
+    pulled += __popc(m);
+    while (m) {
+      long long r[4];
+      int nr = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        r[i] = -1;
+        if (m) r[i] = (w * 32 + (__ffs(m) - 1)) * row_vecs, m &= m - 1, ++nr;
+      }
+      for (int v = lane; v < row_vecs; v += 32) {
+        uint4 val[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nr) val[i] = __ldcv(src + r[i] + v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nr) dst[r[i] + v] = val[i];
+      }
+    }
+  }
+  if (lane == 0 && pulled) atomicAdd(hdr, pulled);
+}
+
+// Weight lines (L*G floats = line_vecs 16-byte vectors) of the valid samples.
+__global__ void dfa_host_pull_weights_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst,
+                                             const uint8_t *__restrict__ svalid, long long nvecs, int line_vecs,
+                                             unsigned long long *__restrict__ hdr) {
+  unsigned long long pulled = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvecs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (svalid[i / line_vecs]) dst[i] = __ldcv(src + i), ++pulled;
+  }
+  for (int m = 16; m; m >>= 1) pulled += __shfl_xor_sync(0xffffffffu, pulled, m);
+  if ((threadIdx.x & 31) == 0 && pulled) atomicAdd(hdr + 1, pulled);
+}
+
 }  // namespace
 
 #include "dfa_forward_win.cuh"
-#include "dfa_forward_gs.cuh"
 
 namespace {
 
@@ -764,40 +850,6 @@ int launch_fwd_win(const void *feat, const int *shape, const int *start, const f
   return static_cast<int>(cudaGetLastError());
 }
 
-// Group-sliced, anchor-pooled kernel: the grid is a whole number of waves of resident CTAs; a block of
-// M anchors x G group CTAs.  DFA_FWD_GS_M = anchors per block the launcher aims at (default 8).
-template <typename T, int LPS, int U, bool TMA, int MINB>
-int launch_fwd_gs(const void *feat, const int *shape, const int *start, const float *loc, const float *w,
-                  float *out, const Dims &d, int interleave, cudaStream_t st) {
-  auto kern = dfa_fwd_gs_kernel<T, LPS, U, TMA, MINB>;
-  const long long total = static_cast<long long>(d.bs) * d.A;
-  const int sms = device_sm_count();
-  if (sms <= 0) return DFA_ERR_UNSUPPORTED;
-  int m_target = DFA_KNOB("DFA_FWD_GS_M", 8);
-  m_target = m_target < 1 ? 1 : (m_target > GS_MMAX - 1 ? GS_MMAX - 1 : m_target);
-  for (int cps = MINB; cps >= 1; --cps) {
-    const long long bpw = static_cast<long long>(sms) * cps / d.G;  // blocks per wave
-    if (bpw < 1) return DFA_ERR_UNSUPPORTED;
-    long long waves = (2 * total + bpw * m_target) / (2 * bpw * m_target);  // nearest whole number
-    if (waves < 1) waves = 1;
-    long long nblocks = waves * bpw < total ? waves * bpw : total;
-    long long mmax = (total + nblocks - 1) / nblocks;
-    if (mmax > GS_MMAX) {  // far fewer resident CTAs than expected: more waves of full-size blocks
-      nblocks = (total + GS_MMAX - 1) / GS_MMAX;
-      mmax = (total + nblocks - 1) / nblocks;
-    }
-    const GsLayout lay = gs_layout(d.P, d.K, d.L, static_cast<int>(mmax), d.C / d.G);
-    if ((static_cast<long long>(lay.total) + 1024) * cps > 227ll * 1024 && cps > 1) continue;
-    if (8ll * d.P * d.K * mmax >= (1ll << 20) || nblocks * d.G >= (1ll << 31)) return DFA_ERR_UNSUPPORTED;
-    if (int rc = set_smem(kern, lay.total)) return rc;
-    kern<<<static_cast<unsigned int>(nblocks * d.G), GS_NT, lay.total, st>>>(
-        static_cast<const T *>(feat), shape, start, loc, w, out, d, static_cast<int>(nblocks),
-        static_cast<int>(mmax), interleave);
-    return static_cast<int>(cudaGetLastError());
-  }
-  return DFA_ERR_UNSUPPORTED;
-}
-
 template <typename T>
 int forward_typed(const void *feat, const int *shape, const int *start, const float *loc,
                   const float *w, float *out, const Dims &d, cudaStream_t st) {
@@ -838,32 +890,6 @@ int forward_typed(const void *feat, const int *shape, const int *start, const fl
         default: return WIN(4, 8);
       }
 #undef WIN
-    }
-  }
-  if (variant >= 50 && variant < 60) {  // group-sliced, anchor-pooled kernel
-    const int lps = gs_lps<T>(d, feat, out);
-    if (lps) {
-      const bool tma = tma_ok(d, loc, w);
-      const int il = variant == 51 ? 1 : 0;
-      const int u = DFA_KNOB("DFA_FWD_GS_U", 4);
-      const int minb = DFA_KNOB("DFA_FWD_GS_MINB", 6);
-#define GS3(LPS, U, MINB)                                                                          \
-  (tma ? launch_fwd_gs<T, LPS, U, true, MINB>(feat, shape, start, loc, w, out, d, il, st)            \
-       : launch_fwd_gs<T, LPS, U, false, MINB>(feat, shape, start, loc, w, out, d, il, st))
-#define GS2(LPS, U) GS3(LPS, U, 6)
-#define GS(LPS)                                                                                    \
-  (minb == 5 ? (u == 6 ? GS3(LPS, 6, 5) : GS3(LPS, 4, 5))                                          \
-             : minb == 4 ? (u == 8 ? GS3(LPS, 8, 4) : GS3(LPS, 6, 4))                              \
-                         : (u == 2 ? GS3(LPS, 2, 6) : u == 3 ? GS3(LPS, 3, 6) : GS3(LPS, 4, 6)))
-      switch (lps) {
-        case 8: return GS(8);
-        case 4: return GS(4);
-        case 2: return GS2(2, 4);
-        default: return GS2(1, 4);
-      }
-#undef GS3
-#undef GS
-#undef GS2
     }
   }
   const int rvariant = variant >= 5 ? 1 : variant;
@@ -1016,14 +1042,25 @@ int dfa_debug_indices(const int32_t *spatial_shape, const int32_t *scale_start_i
   return static_cast<int>(cudaGetLastError());
 }
 
+// Device pointer aliasing a pinned, mapped host buffer (NULL when the buffer is pageable or not mapped).
+static const void *host_alias(const void *h) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (at.type == cudaMemoryTypeHost && at.devicePointer) ? at.devicePointer : nullptr;
+}
+
 int64_t dfa_forward_host_workspace_bytes(int feat_dtype, const dfa_dims *dims) {
   Dims d;
   if (check_dims(dims, d)) return -1;
   const int64_t esz = feat_dtype == DFA_BF16 ? 2 : 4;
   auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  const int64_t rows = static_cast<int64_t>(d.bs) * d.num_feat;
   return up(esz * d.bs * d.num_feat * d.C) + up(8ll * d.K * d.L) + up(4ll * d.K * d.L) +
          up(8ll * d.bs * d.A * d.P * d.K) + up(4ll * d.bs * d.A * d.P * d.K * d.L * d.G) +
-         up(4ll * d.bs * d.A * d.C);
+         up(4ll * d.bs * d.A * d.C) + 256 + up((rows + 31) / 32 * 4) + up(1ll * d.bs * d.A * d.P * d.K);
 }
 
 int dfa_forward_host(const void *h_feat, int feat_dtype, const int32_t *h_shape,
@@ -1042,23 +1079,82 @@ int dfa_forward_host(const void *h_feat, int feat_dtype, const int32_t *h_shape,
   const int64_t nb_feat = esz * d.bs * d.num_feat * d.C, nb_shape = 8ll * d.K * d.L,
                 nb_start = 4ll * d.K * d.L, nb_loc = 8ll * d.bs * d.A * d.P * d.K,
                 nb_w = 4ll * d.bs * d.A * d.P * d.K * d.L * d.G, nb_out = 4ll * d.bs * d.A * d.C;
+  const int64_t rows = static_cast<int64_t>(d.bs) * d.num_feat, nwords = (rows + 31) / 32;
+  const int64_t nsamples = static_cast<int64_t>(d.bs) * d.A * d.P * d.K;
   void *d_feat = p; p += up(nb_feat);
   int32_t *d_shape = reinterpret_cast<int32_t *>(p); p += up(nb_shape);
   int32_t *d_start = reinterpret_cast<int32_t *>(p); p += up(nb_start);
   float *d_loc = reinterpret_cast<float *>(p); p += up(nb_loc);
   float *d_w = reinterpret_cast<float *>(p); p += up(nb_w);
-  float *d_out = reinterpret_cast<float *>(p);
+  float *d_out = reinterpret_cast<float *>(p); p += up(nb_out);
+  unsigned long long *d_hdr = reinterpret_cast<unsigned long long *>(p); p += 256;
+  uint32_t *d_bitmap = reinterpret_cast<uint32_t *>(p); p += up(nwords * 4);
+  uint8_t *d_svalid = reinterpret_cast<uint8_t *>(p);
   cudaError_t e;
-  // small operands first so the kernel's staging data is resident before the big copy ends
+  // Pull mode (default when it applies; DFA_HOST_PULL=0 forces whole copies): the feature table is
+  // pinned + mapped host memory and a row is a whole number of 16-byte vectors.
+  const int64_t row_bytes = esz * d.C, line_bytes = 4ll * d.L * d.G;
+  const void *a_feat = (DFA_KNOB("DFA_HOST_PULL", 1) && row_bytes % 16 == 0 && aligned(h_feat, 16))
+                           ? host_alias(h_feat) : nullptr;
+  const void *a_w = (a_feat && line_bytes % 16 == 0 && aligned(h_w, 16)) ? host_alias(h_w) : nullptr;
+  // small operands first so the kernel's staging data is resident before the big transfer ends
   if ((e = cudaMemcpyAsync(d_shape, h_shape, nb_shape, cudaMemcpyHostToDevice, st))) return e;
   if ((e = cudaMemcpyAsync(d_start, h_start, nb_start, cudaMemcpyHostToDevice, st))) return e;
   if ((e = cudaMemcpyAsync(d_loc, h_loc, nb_loc, cudaMemcpyHostToDevice, st))) return e;
-  if ((e = cudaMemcpyAsync(d_w, h_w, nb_w, cudaMemcpyHostToDevice, st))) return e;
-  if ((e = cudaMemcpyAsync(d_feat, h_feat, nb_feat, cudaMemcpyHostToDevice, st))) return e;
+  if (a_feat) {
+    const int sms = device_sm_count() > 0 ? device_sm_count() : 132;
+    if ((e = cudaMemsetAsync(d_hdr, 0, 256 + up(nwords * 4), st))) return e;  // header + bitmap (adjacent)
+    const unsigned long long fixed = nb_shape + nb_start + nb_loc + (a_w ? 0 : nb_w);
+    const int mark_blocks = static_cast<int>((nsamples + 255) / 256 < sms * 8 ? (nsamples + 255) / 256 : sms * 8);
+    dfa_host_mark_kernel<<<mark_blocks, 256, 0, st>>>(d_shape, d_start, d_loc, d_bitmap, d_svalid, d_hdr,
+                                                      static_cast<unsigned long long>(row_bytes), fixed, d);
+    if ((e = cudaGetLastError())) return e;
+    if (a_w) {
+      const int64_t nvecs = nb_w / 16;
+      const int wb = static_cast<int>((nvecs + 255) / 256 < sms * 16 ? (nvecs + 255) / 256 : sms * 16);
+      dfa_host_pull_weights_kernel<<<wb, 256, 0, st>>>(static_cast<const uint4 *>(a_w), reinterpret_cast<uint4 *>(d_w),
+                                                       d_svalid, nvecs, static_cast<int>(line_bytes / 16), d_hdr);
+      if ((e = cudaGetLastError())) return e;
+    } else if ((e = cudaMemcpyAsync(d_w, h_w, nb_w, cudaMemcpyHostToDevice, st))) {
+      return e;
+    }
+    const int rb = static_cast<int>((nwords + 7) / 8 < sms * 8 ? (nwords + 7) / 8 : sms * 8);
+    dfa_host_pull_rows_kernel<<<rb, 256, 0, st>>>(static_cast<const uint4 *>(a_feat), static_cast<uint4 *>(d_feat),
+                                                  d_bitmap, nwords, rows, static_cast<int>(row_bytes / 16), d_hdr);
+    if ((e = cudaGetLastError())) return e;
+  } else {
+    const unsigned long long hdr[4] = {static_cast<unsigned long long>(rows), static_cast<unsigned long long>(nb_w / 16),
+                                       static_cast<unsigned long long>(row_bytes),
+                                       static_cast<unsigned long long>(nb_shape + nb_start + nb_loc)};
+    if ((e = cudaMemcpyAsync(d_hdr, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st))) return e;
+    if ((e = cudaMemcpyAsync(d_w, h_w, nb_w, cudaMemcpyHostToDevice, st))) return e;
+    if ((e = cudaMemcpyAsync(d_feat, h_feat, nb_feat, cudaMemcpyHostToDevice, st))) return e;
+  }
   if (int rc = dfa_forward(d_feat, feat_dtype, d_shape, d_start, d_loc, d_w, d_out, dims, stream))
     return rc;
   if ((e = cudaMemcpyAsync(h_out, d_out, nb_out, cudaMemcpyDeviceToHost, st))) return e;
   return static_cast<int>(cudaStreamSynchronize(st));
+}
+
+int dfa_forward_host_stats(const void *workspace, int feat_dtype, const dfa_dims *dims, void *stream,
+                           int64_t *h2d_bytes, int64_t *rows_moved, int64_t *weight_bytes_moved) {
+  if (!workspace || !h2d_bytes) return DFA_ERR_NULL_POINTER;
+  Dims d;
+  if (int rc = check_dims(dims, d)) return rc;
+  const int64_t esz = feat_dtype == DFA_BF16 ? 2 : 4;
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  const char *p = static_cast<const char *>(workspace);
+  p += up(esz * d.bs * d.num_feat * d.C) + up(8ll * d.K * d.L) + up(4ll * d.K * d.L) +
+       up(8ll * d.bs * d.A * d.P * d.K) + up(4ll * d.bs * d.A * d.P * d.K * d.L * d.G) + up(4ll * d.bs * d.A * d.C);
+  unsigned long long hdr[4];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(hdr, p, sizeof(hdr), cudaMemcpyDeviceToHost, st))) return e;
+  if ((e = cudaStreamSynchronize(st))) return e;
+  *h2d_bytes = static_cast<int64_t>(hdr[0] * hdr[2] + hdr[1] * 16 + hdr[3]);
+  if (rows_moved) *rows_moved = static_cast<int64_t>(hdr[0]);
+  if (weight_bytes_moved) *weight_bytes_moved = static_cast<int64_t>(hdr[1] * 16);
+  return 0;
 }
 
 }  // extern "C"

@@ -160,7 +160,7 @@ def test_r50_shape_rig_vs_oracle():
     check_case(synthetic.rig_op_inputs(bs=2, seed=3))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 30, 31, 32, 33, 50, 51])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 30, 31, 32, 33])
 def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
     """DFA_FWD_VARIANT selects the forward kernel family / tuning point; all of them must agree
     with the oracle (fp32 and bf16 feature tables, sparse rig and dense uniform locations)."""
@@ -179,39 +179,6 @@ def test_every_forward_kernel_variant_vs_oracle(variant, monkeypatch):
             ref = oracle.forward(g["feat"].float().cpu(), d["spatial_shape"], d["scale_start_index"],
                                  d["sampling_location"], d["weights"])
             assert_close(out, ref, RTOL_F32, "variant %d %s" % (variant, dtype))
-
-
-@pytest.mark.parametrize("m_target,u", [(1, 4), (3, 2), (8, 4), (8, 6), (31, 4)])
-def test_group_sliced_forward_blocks(m_target, u, monkeypatch):
-    """Group-sliced, anchor-pooled forward (DFA_FWD_VARIANT=50/51): a CTA = one channel group of a block of
-    M anchors, the block's taps dealt to the warps in equal ranges.  Every block size and both anchor
-    orders must agree with the oracle on NaN-prefilled outputs — anchors without a valid sample (zeros),
-    anchors cut by a range boundary (partial rows), dense inputs (several passes), blocks spanning batch
-    items, odd sizes without TMA — and repeat bit for bit."""
-    from simpb_b200 import cabi, synthetic
-    monkeypatch.setenv("DFA_FWD_GS_M", str(m_target))
-    monkeypatch.setenv("DFA_FWD_GS_U", str(u))
-    empty = synthetic.rig_op_inputs(bs=2, A=45, seed=61)
-    empty["sampling_location"][0, 3:9] = -0.25          # six anchors in a row without a valid sample
-    empty["sampling_location"][1, 44] = 1.5              # and the very last one
-    cases = [synthetic.rig_op_inputs(bs=1, A=900, seed=62), empty,
-             synthetic.op_inputs_uniform(bs=1, A=70, seed=63),
-             small_case(64, bs=3, A=11, P=13, K=6, sizes=SIZES3, C=256, G=8),
-             small_case(65, bs=1, A=5, P=3, K=3, sizes=SIZES3, C=256, G=8),      # odd P*K: no TMA
-             small_case(66, bs=2, A=7, P=5, K=3, sizes=SIZES3, C=32, G=2),
-             small_case(67, bs=1, A=9, P=4, K=2, sizes=SIZES3, C=64, G=8)]
-    for variant in ("50", "51"):
-        monkeypatch.setenv("DFA_FWD_VARIANT", variant)
-        for d in cases:
-            for dtype in (torch.float32, torch.bfloat16):
-                g = dev(d, dtype)
-                ref = oracle.forward(g["feat"].float().cpu(), d["spatial_shape"], d["scale_start_index"],
-                                     d["sampling_location"], d["weights"])
-                bs, A = d["sampling_location"].shape[:2]
-                junk = torch.full((bs, A, g["feat"].shape[2]), float("nan"), device="cuda")
-                out = cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=junk)
-                assert_close(out, ref, RTOL_F32, "gs variant %s M=%d U=%d %s" % (variant, m_target, u, dtype))
-                assert torch.equal(out, cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"]))
 
 
 @pytest.mark.parametrize("anchors", [900, 950, 889])
@@ -584,6 +551,48 @@ def test_host_buffer_entry_point():
     ref = oracle.forward(d["mc_ms_feat"], d["spatial_shape"], d["scale_start_index"],
                          d["sampling_location"], d["weights"])
     assert_close(h_out, ref, RTOL_F32, "dfa_forward_host")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_host_buffer_pull_mode_moves_exactly_what_the_forward_reads(dtype, monkeypatch):
+    """dfa_forward_host with pinned (mapped) host buffers pulls only the feature rows and weight lines the
+    forward reads.  The result must be bit-identical to the whole-copy path (pageable buffers, and pinned
+    ones with DFA_HOST_PULL=0) — also when the workspace still holds OTHER data from a previous call — and
+    the number of rows pulled must equal the oracle's count of distinct referenced rows."""
+    from simpb_b200 import cabi, synthetic
+    cases = [synthetic.rig_op_inputs(bs=2, A=300, seed=71),
+             small_case(72, bs=2, A=9, P=13, K=6, sizes=SIZES3, C=256, G=8),
+             small_case(73, bs=1, A=5, P=3, K=3, sizes=SIZES3, C=64, G=8)]
+    for ci, d in enumerate(cases):
+        bs, A, P, K = d["sampling_location"].shape[:4]
+        L, G = d["weights"].shape[4:6]
+        C = d["mc_ms_feat"].shape[2]
+        dims = cabi.Dims(bs, K, d["num_feat"], C, L, A, P, G)
+        hf = cabi.HostForward(dims, dtype)
+        hf.workspace.fill_(0xFF)                                  # stale garbage (NaN patterns) everywhere
+        host = [d["mc_ms_feat"].to(dtype).contiguous(), d["spatial_shape"].int().contiguous(),
+                d["scale_start_index"].int().contiguous(), d["sampling_location"].contiguous(),
+                d["weights"].contiguous()]
+        pinned = [t.pin_memory() for t in host]
+        out_pull = hf(*pinned, torch.empty(bs, A, C).pin_memory()).clone()
+        h2d, rows, wbytes = hf.stats()
+        U = oracle.distinct_rows(d["spatial_shape"], d["scale_start_index"], d["sampling_location"], d["num_feat"])
+        valid = ((d["sampling_location"] > 0) & (d["sampling_location"] < 1)).all(-1).sum().item()
+        assert rows == U and wbytes == valid * L * G * 4
+        small = sum(t.numel() * t.element_size() for t in host[1:4])
+        assert h2d == rows * C * host[0].element_size() + wbytes + small
+        if ci == 0:      # camera-rig inputs: most of the table is never referenced
+            assert h2d < 0.5 * sum(t.numel() * t.element_size() for t in host)
+        hf.workspace.fill_(0xFF)
+        out_copy = hf(*host, torch.empty(bs, A, C)).clone()       # pageable: whole copies
+        assert hf.stats()[1] == bs * d["num_feat"]
+        monkeypatch.setenv("DFA_HOST_PULL", "0")
+        out_copy2 = hf(*pinned, torch.empty(bs, A, C).pin_memory()).clone()
+        monkeypatch.delenv("DFA_HOST_PULL")
+        assert torch.equal(out_pull, out_copy) and torch.equal(out_pull, out_copy2)
+        ref = oracle.forward(host[0].float(), d["spatial_shape"], d["scale_start_index"],
+                             d["sampling_location"], d["weights"])
+        assert_close(out_pull, ref, RTOL_F32, "dfa_forward_host pull mode")
 
 
 # ------------------------------------------------------------------ flatten / key points

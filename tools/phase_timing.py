@@ -62,10 +62,7 @@ torch.cuda.synchronize()
 t = buf.cpu().double()
 t = t[t[:, 0, 0] > 0]       # CTAs that ran
 rows_like = a.variant < 10 or a.variant >= 30
-if a.variant >= 50:    # group-sliced, anchor-pooled kernel
-    names = ["0 start", "1 locations landed, compaction, prefix", "2 records built", "3 segments + barrier",
-             "4 gather done", "5 end", "-", "-"]
-elif a.variant >= 40:    # channel-sliced kernel
+if a.variant >= 40:    # channel-sliced kernel
     names = ["0 start", "1 locations landed, camera masks", "2 barrier + plan (+ weights landed)", "3 fine rows built, barrier",
              "4 gather done", "5 end", "-", "-"]
 elif a.variant >= 30:    # window-merging kernel
