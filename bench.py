@@ -670,6 +670,7 @@ def extras(args, cabi, host, peak, roof):
         import frame_bench
         fr = frame_bench.run(frames=8, warmup=3)
         fr["whole_frame_cuda_graph"] = frame_bench.run_graph(frames=30, warmup=4)
+        fr["whole_frame_cuda_graph_folded_bn"] = frame_bench.run_graph(frames=30, warmup=4, fold_bn=True)
         roof["frame"] = fr
     except Exception as e:  # pragma: no cover
         roof["frame"] = {"error": repr(e)}

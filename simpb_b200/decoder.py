@@ -478,6 +478,24 @@ class SimPBFrame(nn.Module):
         self.neck = FPN()
         self.head = FrameDecoder(seed=seed, static_queries=static_queries)
 
+    def fold_batchnorm(self):
+        """Deployment transform (eval only): every BatchNorm of the ResNet is folded into the convolution in
+        front of it (torch.nn.utils.fusion.fuse_conv_bn_eval), which removes 53 normalisation kernels — 1.9 ms
+        of a 13.4 ms frame on B200.  Same function up to rounding; the reference (mmdet ResNet in eval mode)
+        does not do this, so frame_bench reports both."""
+        from torch.nn.utils.fusion import fuse_conv_bn_eval
+        assert not self.training
+        self.stem[0] = fuse_conv_bn_eval(self.stem[0], self.stem[1])
+        self.stem[1] = nn.Identity()
+        for stage in self.stages:
+            for blk in stage:
+                for c, b in (("conv1", "bn1"), ("conv2", "bn2"), ("conv3", "bn3")):
+                    setattr(blk, c, fuse_conv_bn_eval(getattr(blk, c), getattr(blk, b)))
+                    setattr(blk, b, nn.Identity())
+                if blk.downsample is not None:
+                    blk.downsample = nn.Sequential(fuse_conv_bn_eval(blk.downsample[0], blk.downsample[1]))
+        return self
+
     def extract_feat(self, img):
         bs, K = img.shape[:2]
         with torch.autocast("cuda", dtype=torch.float16):

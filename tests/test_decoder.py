@@ -70,3 +70,20 @@ def test_frames_run_and_static_frame_matches_eager():
     for (a0, c0), (a1, c1) in zip(outs[None][1:], outs[320][1:]):
         assert abs(float(c0.mean() - c1.mean())) < 2e-2 * float(c0.abs().mean())
         assert abs(float(a0[..., :3].abs().mean() - a1[..., :3].abs().mean())) < 5e-2 * float(a0[..., :3].abs().mean())
+
+
+@pytest.mark.gpu
+def test_folded_batchnorm_is_the_same_backbone():
+    from simpb_b200 import decoder
+    torch.manual_seed(0)
+    m = decoder.SimPBFrame(seed=2).cuda().eval()
+    for mod in m.modules():          # non-trivial running statistics
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1)
+            mod.running_var.uniform_(0.5, 1.5)
+    img = torch.randn(1, 6, 3, 256, 704, device="cuda")
+    with torch.no_grad():
+        ref = m.extract_feat(img)[0]
+        out = m.fold_batchnorm().extract_feat(img)[0]
+    assert not any(isinstance(x, torch.nn.BatchNorm2d) for x in m.modules())
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-2      # fp16 autocast on both sides

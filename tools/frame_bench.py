@@ -77,11 +77,18 @@ def run(frames=12, warmup=4, seed=0, breakdown=True):
     return rec
 
 
-def run_graph(frames=30, warmup=4, seed=0, cap=320):
+def run_graph(frames=30, warmup=4, seed=0, cap=320, fold_bn=False, tf32=False):
     """The whole frame as ONE CUDA graph (static 2-D query slots).  Per frame: H2D copy of the six images
-    from pinned memory + the ego-motion inputs, one graph replay, D2H of the classification scores."""
+    from pinned memory + the ego-motion inputs, one graph replay, D2H of the classification scores.
+    fold_bn: BatchNorm folded into the convolutions (deployment transform).  tf32: fp32 matrix products of
+    the decoder's nn.Linear / attention projections on the tensor cores (torch's allow_tf32; NOT the
+    reference's arithmetic — reported separately)."""
     dev = "cuda"
     model = decoder.SimPBFrame(seed=seed, static_queries=cap).to(dev).eval()
+    if fold_bn:
+        model.fold_batchnorm()
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
     proj, wh = synthetic.camera_rig(1)
     gen = torch.Generator().manual_seed(seed)
     host_imgs = [torch.randn(1, 6, 3, 256, 704, generator=gen).pin_memory() for _ in range(3)]
@@ -113,10 +120,12 @@ def run_graph(frames=30, warmup=4, seed=0, cap=320):
             if i >= warmup:
                 times.append(e0.elapsed_time(e1))
     ms = statistics.median(times)
+    torch.backends.cuda.matmul.allow_tf32 = old_tf32
     assert torch.isfinite(host_cls).all()
     return {"workload": "same frame as ONE CUDA-graph replay: %d static 2-D query slots per camera (%d queries), "
-                        "images copied from pinned host memory and class scores copied back inside the frame"
-                        % (cap, 6 * cap),
+                        "images copied from pinned host memory and class scores copied back inside the frame%s%s"
+                        % (cap, 6 * cap, "; BatchNorm folded into the convolutions" if fold_bn else "",
+                           "; fp32 matrix products in TF32 (not the reference's arithmetic)" if tf32 else ""),
             "frames_per_sec": 1e3 / ms, "ms_per_frame": ms, "frames_timed": frames, "warmup_frames": warmup,
             "h2d_bytes_per_frame": img.numel() * 4, "d2h_bytes_per_frame": host_cls.numel() * 4}
 
@@ -133,4 +142,6 @@ if __name__ == "__main__":
         rec["eager"] = run(a.frames, a.warmup, breakdown=not a.no_breakdown)
     if a.mode in ("graph", "both"):
         rec["graph"] = run_graph(max(a.frames, 30), a.warmup)
+        rec["graph_folded_bn"] = run_graph(max(a.frames, 30), a.warmup, fold_bn=True)
+        rec["graph_folded_bn_tf32"] = run_graph(max(a.frames, 30), a.warmup, fold_bn=True, tf32=True)
     print(json.dumps(rec))
