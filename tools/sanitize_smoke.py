@@ -38,6 +38,19 @@ for bv in ("10", "11", "12", "0"):
             f, sh, st, loc, w, go = dev(d, dt)
             cabi.backward(f, sh, st, loc, w, go)
             cabi.backward(f, sh, st, loc, w, go, need_feat=False)
+# host-buffer entry point: pull mode (pinned, mapped buffers) and whole copies (pageable)
+for d in cases[:3]:
+    for dt in (torch.float32, torch.bfloat16):
+        bs, A, P, K = d["sampling_location"].shape[:4]
+        L, G = d["weights"].shape[4:6]
+        C = d["mc_ms_feat"].shape[2]
+        hf = cabi.HostForward(cabi.Dims(bs, K, d["num_feat"], C, L, A, P, G), dt)
+        host = [d["mc_ms_feat"].to(dt).contiguous(), d["spatial_shape"].int().contiguous(),
+                d["scale_start_index"].int().contiguous(), d["sampling_location"].contiguous(), d["weights"].contiguous()]
+        a = hf(*[t.pin_memory() for t in host], torch.empty(bs, A, C).pin_memory()).clone()
+        b = hf(*host, torch.empty(bs, A, C))
+        assert torch.equal(a, b), "pull mode differs from whole copies"
+        hf.stats()
 torch.cuda.synchronize()
 print("op kernels done")
 
