@@ -234,6 +234,13 @@ class DeformableFeatureAggregation(nn.Module):
         kps_generator["embed_dims"] = embed_dims
         self.kps_generator = build_kps_generator(kps_generator)
         self.num_pts = self.kps_generator.num_pts
+        # The attention-weight kernels (csrc/dfa_frontend.cu) stage one anchor's K*L*P*G logits in shared
+        # memory and reduce groups with 256-thread blocks; say so here instead of failing inside forward()
+        # (the reference accepts any embed_dims % num_groups == 0; there is no eager fallback by design).
+        n_logits = num_cams * num_levels * self.num_pts * num_groups
+        if 256 % num_groups != 0 or num_cams * num_levels * self.num_pts >= 65536 or 4 * n_logits > 190 * 1024:
+            raise ValueError("DeformableFeatureAggregation: num_groups must divide 256 and one anchor's "
+                             "K*L*P*G = %d attention logits must fit 190 KB of shared memory" % n_logits)
         # upstream builds temporal_fusion_module and never calls it in forward (:83-90); only an
         # already-built module is accepted here so that checkpoints with such keys still load
         self.temp_module = temporal_fusion_module if isinstance(temporal_fusion_module, nn.Module) else None

@@ -162,7 +162,7 @@ __host__ __device__ inline SmemLayout2 smem_layout2(int P, int K, int L, int G, 
   s.loc = o, o = align_up(o + 8u * P * K, 16);
   s.off = o, o = align_up(o + 16u * taps, 16);
   s.bw = o, o = align_up(o + 16u * taps, 16);
-  s.widx = o, o = align_up(o + 4u * taps, 16);
+  s.widx = o, o = align_up(o + 2u * taps, 16);  // 16-bit: rows_vpr() checks P*K*L*G < 65536
   s.list = o, o = align_up(o + 4u * P * K, 16);
   s.tab = o, o = align_up(o + 12u * K * L, 16);
   s.red = o, o = align_up(o + 4u * slices * C, 16);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NT, MINB)
   float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
   uint4 *s_off = reinterpret_cast<uint4 *>(smem + lay.off);
   float4 *s_bw = reinterpret_cast<float4 *>(smem + lay.bw);
-  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  uint16_t *s_widx = reinterpret_cast<uint16_t *>(smem + lay.widx);
   int *s_list = reinterpret_cast<int *>(smem + lay.list);
   int *s_tab = reinterpret_cast<int *>(smem + lay.tab);
   float *s_red = reinterpret_cast<float *>(smem + lay.red);
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(NT, MINB)
     off.y = (gm.row[1] >= 0 ? gm.row[1] : safe) * rb, bw.y = gm.row[1] >= 0 ? live * gm.hh * gm.lw : 0.f;
     off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, bw.z = gm.row[2] >= 0 ? live * gm.lh * gm.hw : 0.f;
     off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, bw.w = gm.row[3] >= 0 ? live * gm.lh * gm.lw : 0.f;
-    s_off[t] = off, s_bw[t] = bw, s_widx[t] = (s * d.L + l) * d.G;
+    s_off[t] = off, s_bw[t] = bw, s_widx[t] = static_cast<uint16_t>((s * d.L + l) * d.G);
   }
   DFA_STAMP(2);
   __syncthreads();
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(NT, MINB)
   float *s_loc = reinterpret_cast<float *>(smem + lay.loc);
   uint4 *s_off = reinterpret_cast<uint4 *>(smem + lay.off);
   float4 *s_bw = reinterpret_cast<float4 *>(smem + lay.bw);
-  int *s_widx = reinterpret_cast<int *>(smem + lay.widx);
+  uint16_t *s_widx = reinterpret_cast<uint16_t *>(smem + lay.widx);
   int *s_list = reinterpret_cast<int *>(smem + lay.list);
   int *s_tab = reinterpret_cast<int *>(smem + lay.tab);
   float *s_red = reinterpret_cast<float *>(smem + lay.red);
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(NT, MINB)
     off.y = (gm.row[1] >= 0 ? gm.row[1] : safe) * rb, bw.y = gm.row[1] >= 0 ? live * gm.hh * gm.lw : 0.f;
     off.z = (gm.row[2] >= 0 ? gm.row[2] : safe) * rb, bw.z = gm.row[2] >= 0 ? live * gm.lh * gm.hw : 0.f;
     off.w = (gm.row[3] >= 0 ? gm.row[3] : safe) * rb, bw.w = gm.row[3] >= 0 ? live * gm.lh * gm.lw : 0.f;
-    s_off[t] = off, s_bw[t] = bw, s_widx[t] = ((k * d.L + l) * d.P + p) * d.G;  // (k,l,p,g) order
+    s_off[t] = off, s_bw[t] = bw, s_widx[t] = static_cast<uint16_t>(((k * d.L + l) * d.P + p) * d.G);  // (k,l,p,g) order
   }
   __syncthreads();
   DFA_STAMP(5);
@@ -823,6 +823,7 @@ int rows_vpr(const Dims &d, const void *feat, int nt) {
   const int vpr = d.C / VEC;
   if (vpr > nt || nt % vpr != 0 || (vpr & (vpr - 1)) != 0) return 0;
   if (static_cast<long long>(d.num_feat) * d.C * static_cast<long long>(sizeof(T)) >= (1ll << 32)) return 0;
+  if (static_cast<long long>(d.P) * d.K * d.L * d.G >= 65536) return 0;  // 16-bit weight index per tap
   return vpr;
 }
 
