@@ -314,19 +314,34 @@ def workload_config(args):
 
 # ----------------------------------------------------------------------------- own arm
 def train_step_fns(cabi, sets, outs, bucket):
-    """The training step of the op: forward, backward (grad_mc_ms_feat zero-filled by the library on the
-    stream, the two small gradients written in full), then — with a bucket — the data-parallel
-    all-reduce (mean) of a gradient bucket the size of the three DFA layers' parameters, enqueued on a
-    side stream so that it overlaps the next step's kernels."""
+    """The training step of the op: forward, backward (the two small gradients written in full), then —
+    with a bucket — the data-parallel all-reduce (mean) of a gradient bucket the size of the three DFA
+    layers' parameters, enqueued on a side stream so that it overlaps the next step's kernels.
+    grad_mc_ms_feat has to start from zero (different anchors meet on one pixel): that fill does not
+    depend on the forward, so it runs on a forked stream NEXT TO the forward kernel — a DRAM-write stream
+    beside a gather that leaves two thirds of the DRAM bandwidth idle — and joins before the backward
+    (DFA_BENCH_SERIAL_FILL=1: the library's own fill in front of the backward kernel, as in round 1)."""
     gfs = [torch.empty_like(g["feat"], dtype=torch.float32) for g in sets[:1]]
     gls = [torch.empty_like(g["loc"]) for g in sets]
     gws = [torch.empty_like(g["w"]) for g in sets]
+    serial = os.environ.get("DFA_BENCH_SERIAL_FILL", "0") == "1"
+    side = torch.cuda.Stream()
 
     def mk(i, g, o):
         def f():
-            cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o)
-            cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
-                          gfs[0], gls[i], gws[i], flags=cabi.BWD_OVERWRITE_SMALL | cabi.BWD_ZERO_GRAD_FEAT)
+            if serial:
+                cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o)
+                cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
+                              gfs[0], gls[i], gws[i], flags=cabi.BWD_OVERWRITE_SMALL | cabi.BWD_ZERO_GRAD_FEAT)
+            else:
+                cur = torch.cuda.current_stream()
+                side.wait_stream(cur)             # after the previous step's backward (it wrote gfs[0])
+                with torch.cuda.stream(side):
+                    gfs[0].zero_()
+                cabi.forward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], out=o)
+                cur.wait_stream(side)
+                cabi.backward(g["feat"], g["shape"], g["start"], g["loc"], g["w"], g["go"],
+                              gfs[0], gls[i], gws[i], flags=cabi.BWD_OVERWRITE_SMALL)
             if bucket is not None:
                 bucket.wait()                 # the previous step's all-reduce must have landed
                 bucket.all_reduce_mean()

@@ -44,6 +44,13 @@ def test_argument_validation_needs_no_gpu():
     assert cabi.lib.dfa_forward(p, 7, p, p, p, p, p, ctypes.byref(d), None) == -3
     assert cabi.lib.dfa_forward(p + 2, 0, p, p, p, p, p, ctypes.byref(d), None) == -4
     assert cabi.lib.dfa_forward_host_workspace_bytes(0, ctypes.byref(d)) > 4 * 100 * 256
+    # host entry point and its statistics: same validation, before any CUDA call
+    assert cabi.lib.dfa_forward_host(p, 0, p, p, p, p, p, ctypes.byref(d), None, 1 << 30, None) == -1
+    assert cabi.lib.dfa_forward_host(p, 0, p, p, p, p, p, ctypes.byref(d), p, 16, None) == -2      # workspace too small
+    assert cabi.lib.dfa_forward_host(p, 9, p, p, p, p, p, ctypes.byref(d), p, 1 << 30, None) == -3
+    n = ctypes.c_int64(0)
+    assert cabi.lib.dfa_forward_host_stats(None, 0, ctypes.byref(d), None, ctypes.byref(n), None, None) == -1
+    assert cabi.lib.dfa_forward_host_stats(p, 0, ctypes.byref(bad), None, ctypes.byref(n), None, None) == -2
 
 
 def test_argument_validation_of_the_other_entry_points():
