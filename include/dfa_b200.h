@@ -189,6 +189,18 @@ int dfa_msda_forward(const void *value, int value_dtype, const int32_t *spatial_
                      const float *attn_weight, float *output, int bs, int num_value, int num_heads,
                      int head_dim, int num_query, int num_levels, int num_points, int num_tables,
                      const int32_t *query_table, void *stream);
+/* Inference variant on the UNPROJECTED table [bs, num_tables, num_value, channels] (no head dimension;
+ * a row is 512 or 1024 bytes): gathers whole rows per (query, head) — out_gathered [bs, num_query,
+ * num_heads, channels] — and the sum of attention x in-map bilinear weights out_weight_sum [bs, num_query,
+ * num_heads], so that the caller applies value_proj AFTER the gather:
+ *   out[b,q,m,:] = W_m . out_gathered[b,q,m,:] + bias_m * out_weight_sum[b,q,m]
+ * (sampling is linear; this replaces the [bs*tables*num_value, C] x [C, C] GEMM of models/group_attn.py:
+ * 172 by num_heads products of [num_query, C] x [C, head_dim]). */
+int dfa_msda_forward_raw(const void *table, int table_dtype, const int32_t *spatial_shapes,
+                         const int32_t *level_start_index, const float *sampling_loc,
+                         const float *attn_weight, float *out_gathered, float *out_weight_sum, int bs,
+                         int num_value, int channels, int num_heads, int num_query, int num_levels,
+                         int num_points, int num_tables, const int32_t *query_table, void *stream);
 int dfa_msda_backward(const void *value, int value_dtype, const int32_t *spatial_shapes,
                       const int32_t *level_start_index, const float *sampling_loc,
                       const float *attn_weight, const float *grad_output, float *grad_value,

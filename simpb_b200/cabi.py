@@ -21,7 +21,7 @@ SYMBOLS = ("dfa_version", "dfa_error_string", "dfa_debug_reload_knobs", "dfa_for
            "dfa_flatten_maps", "dfa_keypoints_project", "dfa_keypoints_project_backward",
            "dfa_softmax_weights", "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
            "dfa_softmax_weights_split_backward",
-           "dfa_msda_forward", "dfa_msda_backward",
+           "dfa_msda_forward", "dfa_msda_backward", "dfa_msda_forward_raw",
            "dfa_forward_host_workspace_bytes", "dfa_forward_host", "dfa_forward_host_stats")
 
 
@@ -65,6 +65,8 @@ def _load():
                                      vp, vp]
     lib.dfa_msda_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                       i32, i32, i32, vp, i32, vp]
+    lib.dfa_msda_forward_raw.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32,
+                                         vp, vp]
     lib.dfa_forward_host_workspace_bytes.restype = i64
     lib.dfa_forward_host_workspace_bytes.argtypes = [i32, dp]
     lib.dfa_forward_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, dp, vp, i64, vp]
@@ -72,8 +74,8 @@ def _load():
     for name in ("dfa_forward", "dfa_backward", "dfa_debug_indices", "dfa_flatten_maps",
                  "dfa_keypoints_project", "dfa_keypoints_project_backward", "dfa_softmax_weights",
                  "dfa_softmax_weights_backward", "dfa_softmax_weights_split",
-                 "dfa_softmax_weights_split_backward", "dfa_msda_forward", "dfa_msda_backward",
-                 "dfa_forward_host", "dfa_forward_host_stats"):
+                 "dfa_softmax_weights_split_backward", "dfa_msda_forward", "dfa_msda_backward", "dfa_msda_forward_raw",
+                 "dfa_forward_host", "dfa_forward_host_stats", "dfa_msda_forward_raw"):
         getattr(lib, name).restype = i32
     return lib
 
@@ -453,6 +455,34 @@ def msda_forward(value, shapes, start, loc, w, query_table=None):
                                    query_table.data_ptr() if query_table is not None else None,
                                    stream_ptr(value.device)), "dfa_msda_forward")
     return out
+
+
+def msda_forward_raw(table, shapes, start, loc, w, query_table=None):
+    """Gather-then-project variant (inference).  table [bs,S,C] or [bs,K,S,C] (UNPROJECTED rows of 512 or
+    1024 bytes), loc [bs,Q,M,L,P,2], w [bs,Q,M,L,P]; returns (gathered [bs,Q,M,C], weight_sum [bs,Q,M]) —
+    the caller applies value_proj per head afterwards (include/dfa_b200.h)."""
+    _need(table, "table")
+    _need(loc, "sampling_locations", torch.float32)
+    _need(w, "attention_weights", torch.float32)
+    if table.dim() not in (3, 4) or loc.dim() != 6 or loc.shape[-1] != 2 or w.shape != loc.shape[:-1]:
+        raise DfaError("msda_forward_raw: table [bs,(K,)S,C], loc [bs,Q,M,L,P,2], w [bs,Q,M,L,P]")
+    K = table.shape[1] if table.dim() == 4 else 1
+    bs, S, C = table.shape[0], table.shape[-2], table.shape[-1]
+    _, Q, M, L, P, _ = loc.shape
+    if loc.shape[0] != bs or shapes.numel() != 2 * L or start.numel() != L:
+        raise DfaError("msda_forward_raw: inconsistent batch size or level tables")
+    if K > 1 and (query_table is None or query_table.numel() != Q or query_table.dtype != torch.int32):
+        raise DfaError("msda_forward_raw: query_table int32 [Q] is required with several tables")
+    g = torch.empty(bs, Q, M, C, device=table.device, dtype=torch.float32)
+    ssum = torch.empty(bs, Q, M, device=table.device, dtype=torch.float32)
+    if bs == 0 or Q == 0:
+        return g, ssum
+    with torch.cuda.device(table.device):
+        check(lib.dfa_msda_forward_raw(table.data_ptr(), feat_dtype(table), shapes.data_ptr(), start.data_ptr(),
+                                       loc.data_ptr(), w.data_ptr(), g.data_ptr(), ssum.data_ptr(), bs, S, C, M,
+                                       Q, L, P, K, query_table.data_ptr() if query_table is not None else None,
+                                       stream_ptr(table.device)), "dfa_msda_forward_raw")
+    return g, ssum
 
 
 def msda_backward(value, shapes, start, loc, w, grad_out, need_value=True, query_table=None):

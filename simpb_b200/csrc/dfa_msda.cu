@@ -405,6 +405,112 @@ int msda_forward_typed(const void *value, const int *shapes, const int *start, c
   return static_cast<int>(cudaGetLastError());
 }
 
+
+// ------------------------------------------------------------------------------------------
+// forward on the UNPROJECTED table (inference): gather first, project afterwards
+// ------------------------------------------------------------------------------------------
+// The module computes value = value_proj(table) for all S rows of every camera (a [bs*K*S, C] x [C, C]
+// GEMM: 11.8 GFLOP per layer at SimPB's size, 0.39 ms in fp32) and then samples M*L*P taps per query
+// from it.  Sampling is linear, so the projection can move behind it:
+//     out[q, m, :] = W_m . ( sum_taps a * bilinear(table) ) + b_m * sum_taps a * (in-map corner weight)
+// Here warp m of the query's CTA gathers the WHOLE rows (C channels) of head m's taps from the raw
+// table: g[b,q,m,:] (C floats) and s[b,q,m] (the sum that multiplies the bias).  The M small
+// [Q, C] x [C, D] products that remain are 126 MFLOP.  The gather moves M times the bytes of the
+// projected one — 0.98 GB per layer from an L2-resident table — and still costs a quarter of the GEMM.
+// VPL: 16-byte vectors per lane per row (row bytes = 512 * VPL).  Two corners' loads of all taps in
+// flight: 4 * VPL loads per lane per tap.
+template <typename T, int VPL, bool TMA>
+__global__ void __launch_bounds__(1024)
+    msda_raw_fwd_kernel(const T *__restrict__ table, const int *__restrict__ shapes,
+                        const int *__restrict__ start, const float *__restrict__ loc,
+                        const float *__restrict__ w, float *__restrict__ out_g, float *__restrict__ out_s,
+                        MsdaDims d, const int *__restrict__ qcam) {
+  constexpr int VEC = FeatVec<T>::VEC;
+  constexpr int C = 32 * VPL * VEC;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int LP = d.L * d.P, n_tap = d.M * LP;
+  float *s_loc = reinterpret_cast<float *>(smem);
+  float *s_w = s_loc + 2 * n_tap;
+  MsdaRec *s_rec = reinterpret_cast<MsdaRec *>(smem + align_up(12u * n_tap, 16));
+  uint64_t *bar = reinterpret_cast<uint64_t *>(s_rec + static_cast<size_t>(d.M) * LP * 4);
+  const int lane = threadIdx.x & 31, m = threadIdx.x >> 5;
+  const long long bq = blockIdx.x;
+  const int b = static_cast<int>(bq / d.Q), q = static_cast<int>(bq - static_cast<long long>(b) * d.Q);
+  msda_stage<TMA>(loc + bq * n_tap * 2, w + bq * n_tap, s_loc, s_w, bar, n_tap);
+
+  MsdaRec *rec = s_rec + static_cast<size_t>(m) * LP * 4;
+  for (int t = lane; t < LP; t += 32) {
+    const int l = t / d.P, i = m * LP + t;
+    const int H = __ldg(shapes + 2 * l), W = __ldg(shapes + 2 * l + 1), s0 = __ldg(start + l);
+    MsdaGeom g;
+    msda_geometry(s_loc[2 * i], s_loc[2 * i + 1], H, W, g);
+    const float aw = s_w[i];
+    const float bw[4] = {g.hh * g.hw, g.hh * g.lw, g.lh * g.hw, g.lh * g.lw};
+    // an out-of-map corner (zero padding) replays an in-map corner of the tap with coefficient 0; a tap
+    // that is not taken at all replays row 0
+    const int safe = g.idx[0] >= 0 ? g.idx[0] : g.idx[1] >= 0 ? g.idx[1] : g.idx[2] >= 0 ? g.idx[2]
+                   : g.idx[3] >= 0 ? g.idx[3] : -s0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      MsdaRec r;
+      r.off = (s0 + (g.idx[c] >= 0 ? g.idx[c] : safe)) * C;
+      r.a = g.idx[c] >= 0 ? bw[c] * aw : 0.f;
+      r.b = r.c = 0.f;
+      rec[4 * t + c] = r;
+    }
+  }
+  __syncwarp();
+
+  const int cam = qcam ? __ldg(qcam + q) : 0;
+  const T *tb = table + (static_cast<size_t>(b) * d.K + cam) * d.S * C + lane * VEC;
+  float acc[VPL][VEC];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[v][c] = 0.f;
+  float ssum = 0.f;
+  for (int t = 0; t < LP; ++t) {
+    typename FeatVec<T>::raw_t val[4][VPL];
+    float cw[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const MsdaRec r = rec[4 * t + c];
+      cw[c] = r.a;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) val[c][v] = FeatVec<T>::load_raw(tb + r.off + v * 32 * VEC);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      ssum += cw[c];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) FeatVec<T>::fma(acc[v], cw[c], val[c][v]);
+    }
+  }
+  float *og = out_g + (bq * d.M + m) * C + lane * VEC;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int c = 0; c < VEC / 4; ++c)
+      reinterpret_cast<float4 *>(og + v * 32 * VEC)[c] =
+          make_float4(acc[v][4 * c], acc[v][4 * c + 1], acc[v][4 * c + 2], acc[v][4 * c + 3]);
+  if (lane == 0) out_s[bq * d.M + m] = ssum;
+}
+
+template <typename T, int VPL>
+int msda_launch_raw(const void *table, const int *shapes, const int *start, const float *loc, const float *w,
+                    float *out_g, float *out_s, const MsdaDims &d, const int *qcam, cudaStream_t st) {
+  const uint32_t smem = align_up(12u * d.M * d.L * d.P, 16) + 16u * 4u * d.M * d.L * d.P + 16u;
+  const long long grid = static_cast<long long>(d.bs) * d.Q;
+  if (smem > 200u * 1024u) return DFA_ERR_UNSUPPORTED;
+  auto go = [&](auto kern) -> int {
+    if (int rc = set_smem(kern, smem)) return rc;
+    kern<<<static_cast<unsigned int>(grid), 32 * d.M, smem, st>>>(static_cast<const T *>(table), shapes, start, loc, w,
+                                                                 out_g, out_s, d, qcam);
+    return static_cast<int>(cudaGetLastError());
+  };
+  return msda_tma_ok(d, loc, w) ? go(msda_raw_fwd_kernel<T, VPL, true>) : go(msda_raw_fwd_kernel<T, VPL, false>);
+}
+
 template <typename T>
 int msda_backward_typed(const void *value, const int *shapes, const int *start, const float *loc,
                         const float *w, const float *go, float *gv, float *gl, float *gw,
@@ -448,6 +554,36 @@ int dfa_msda_forward(const void *value, int value_dtype, const int32_t *spatial_
     return msda_forward_typed<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_loc,
                                              attn_weight, output, d, query_table, st);
   return DFA_ERR_BAD_DTYPE;
+}
+
+int dfa_msda_forward_raw(const void *table, int table_dtype, const int32_t *spatial_shapes,
+                         const int32_t *level_start_index, const float *sampling_loc,
+                         const float *attn_weight, float *out_gathered, float *out_weight_sum, int bs,
+                         int num_value, int channels, int num_heads, int num_query, int num_levels,
+                         int num_points, int num_tables, const int32_t *query_table, void *stream) {
+  if (!table || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !out_gathered ||
+      !out_weight_sum)
+    return DFA_ERR_NULL_POINTER;
+  if (num_tables > 1 && !query_table) return DFA_ERR_NULL_POINTER;
+  MsdaDims d;
+  if (int rc = msda_check(bs, num_value, 1, channels, num_query, num_levels, num_points, num_tables, d)) return rc;
+  if (num_heads <= 0 || num_heads > 32) return DFA_ERR_BAD_DIMS;
+  if (static_cast<long long>(bs) * num_query * num_heads >= (1ll << 31)) return DFA_ERR_BAD_DIMS;
+  d.M = num_heads;  // heads = warps of a query's CTA; the table itself has no head dimension
+  d.D = channels;
+  if (table_dtype != DFA_F32 && table_dtype != DFA_BF16) return DFA_ERR_BAD_DTYPE;
+  const long long rb = static_cast<long long>(channels) * (table_dtype == DFA_BF16 ? 2 : 4);
+  if ((rb != 512 && rb != 1024) || !aligned(table, 16) || !aligned(out_gathered, 16)) return DFA_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (table_dtype == DFA_F32)
+    return rb == 1024 ? msda_launch_raw<float, 2>(table, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                                  out_gathered, out_weight_sum, d, query_table, st)
+                      : msda_launch_raw<float, 1>(table, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                                  out_gathered, out_weight_sum, d, query_table, st);
+  return rb == 1024 ? msda_launch_raw<__nv_bfloat16, 2>(table, spatial_shapes, level_start_index, sampling_loc,
+                                                        attn_weight, out_gathered, out_weight_sum, d, query_table, st)
+                    : msda_launch_raw<__nv_bfloat16, 1>(table, spatial_shapes, level_start_index, sampling_loc,
+                                                        attn_weight, out_gathered, out_weight_sum, d, query_table, st);
 }
 
 int dfa_msda_backward(const void *value, int value_dtype, const int32_t *spatial_shapes,

@@ -10,6 +10,7 @@ view of one camera's rows of the same channel-last table the 3-D branch gathers 
 or bfloat16.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -169,10 +170,21 @@ class QueryGroupMultiScaleDeformableAttention(nn.Module):
         bcs, num_value, _ = value.shape
         if bcs // self.num_cams != bs:
             raise ValueError("value must hold bs*num_cams = %d items, got %d" % (bs * self.num_cams, bcs))
-        value = self.value_proj(value)
-        if key_padding_mask is not None:
-            value = value.masked_fill(key_padding_mask[..., None], 0.0)
-        value = value.view(bs, self.num_cams, num_value, self.num_heads, -1)
+        # Inference on a table whose rows are 512 or 1024 bytes, queries grouped by camera in order: gather
+        # the UNPROJECTED rows per (query, head) and apply value_proj afterwards (sampling is linear) — the
+        # [bs*K*S, C] x [C, C] GEMM over the whole table (0.39 ms per layer at SimPB's size) becomes num_heads
+        # products over the queries only.  SIMPB_B200_MSDA_PROJECT_FIRST=1 keeps the reference's order.
+        raw = None
+        if (not torch.is_grad_enabled() and key_padding_mask is None and value.is_cuda
+                and value.dtype in (torch.float32, torch.bfloat16)
+                and value.shape[-1] * value.element_size() in (512, 1024)
+                and os.environ.get("SIMPB_B200_MSDA_PROJECT_FIRST", "0") != "1"):
+            raw = value.contiguous().view(bs, self.num_cams, num_value, -1)
+        else:
+            value = self.value_proj(value)
+            if key_padding_mask is not None:
+                value = value.masked_fill(key_padding_mask[..., None], 0.0)
+            value = value.view(bs, self.num_cams, num_value, self.num_heads, -1)
         offsets = self.sampling_offsets(query).view(bs, num_query, self.num_heads, self.num_levels,
                                                     self.num_points, 2)
         weights = self.attention_weights(query).view(bs, num_query, self.num_heads,
@@ -186,7 +198,20 @@ class QueryGroupMultiScaleDeformableAttention(nn.Module):
         if kwargs.get("query_groups", None) is not None:
             self.query_groups = kwargs["query_groups"]
         table = self._query_table(num_query, value.device)
-        if table is not None:       # the groups tile [0, num_query) in order: one launch for all cameras
+        if raw is not None and table is None:          # groups out of order: the reference's order after all
+            value = self.value_proj(value).view(bs, self.num_cams, num_value, self.num_heads, -1)
+            raw = None
+        if raw is not None:
+            g, ssum = cabi.msda_forward_raw(raw, _i32(spatial_shapes), _i32(level_start_index),
+                                            loc.contiguous().float(), weights.contiguous().float(), table)
+            M, D = self.num_heads, self.embed_dims // self.num_heads
+            wv = self.value_proj.weight.view(M, D, -1)                                  # [m, d, c]
+            output = torch.bmm(g.view(bs * num_query, M, -1).transpose(0, 1).to(wv.dtype), wv.transpose(1, 2))
+            output = output.transpose(0, 1).reshape(bs, num_query, M, D)
+            if self.value_proj.bias is not None:
+                output = output + ssum[..., None] * self.value_proj.bias.view(M, D)
+            output = output.reshape(bs, num_query, M * D)
+        elif table is not None:     # the groups tile [0, num_query) in order: one launch for all cameras
             output = GroupedMultiScaleDeformableAttnFunction.apply(value, spatial_shapes, level_start_index,
                                                                    loc, weights, table)
         else:                       # anything else: group by group, as the reference (:226-236)

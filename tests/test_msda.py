@@ -255,3 +255,60 @@ def test_autograd_function_and_query_group_module():
     assert_close(v.grad, ref[2], 2e-5, "grad value")
     for n, p in m.named_parameters():
         assert_close(p.grad, ref[3][n], 2e-5, "grad " + n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,heads,dtype", [(256, 8, torch.float32), (128, 4, torch.float32),
+                                           (256, 8, torch.bfloat16)])
+def test_gather_then_project_equals_project_then_gather(C, heads, dtype, monkeypatch):
+    """Inference path of the module: whole rows of the UNPROJECTED table gathered per (query, head)
+    (dfa_msda_forward_raw), value_proj applied afterwards.  Sampling is linear, so the result equals the
+    reference's order (value_proj over the whole table, then sampling) up to fp32 rounding — also for
+    taps on and beyond the border (the bias is weighted by the in-map part only), with a bias that is not
+    zero, for empty camera groups, and against the kernel-level definition of the two outputs."""
+    from simpb_b200 import cabi, msda
+    torch.manual_seed(3)
+    bs, cams = 2, 3
+    sizes = ((8, 12), (4, 6), (2, 3), (1, 2))
+    shapes = torch.tensor(sizes)
+    counts = shapes[:, 0] * shapes[:, 1]
+    start = torch.cat([counts.new_zeros(1), counts.cumsum(0)[:-1]])
+    S = int(counts.sum())
+    groups = [(0, 9), (9, 9), (9, 21)]                    # camera 1 has no query
+    m = msda.QueryGroupMultiScaleDeformableAttention(embed_dims=C, num_heads=heads, num_levels=4, num_points=4,
+                                                     num_cams=cams, query_groups=groups, dropout=0.0,
+                                                     batch_first=True, residual_mode="cat").cuda().eval()
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.3)
+        m.sampling_offsets.bias.mul_(3.0)                  # pushes many taps over the border
+        m.attention_weights.weight.normal_(0, 0.5)
+        m.value_proj.bias.normal_(0, 0.5)
+    g = torch.Generator().manual_seed(4)
+    query = torch.randn(bs, 21, C, generator=g).cuda()
+    table = torch.randn(bs * cams, S, C, generator=g).cuda().to(dtype)
+    ref_pts = torch.rand(bs, 21, 4, 2, generator=g).cuda()
+    kw = dict(reference_points=ref_pts, spatial_shapes=shapes.cuda(), level_start_index=start.cuda())
+    with torch.no_grad():
+        fast = m(query, value=table.float() if dtype == torch.float32 else table, **kw)
+        monkeypatch.setenv("SIMPB_B200_MSDA_PROJECT_FIRST", "1")
+        slow = m(query, value=table.float(), **kw)
+    tol = RTOL_F32 if dtype == torch.float32 else RTOL_BF16
+    assert_close(fast, slow, tol, "gather-then-project vs project-then-gather")
+    if dtype != torch.float32:
+        return
+    # the kernel's two outputs against their definition, head by head, through the projected kernel:
+    # with W = identity blocks the projected kernel returns the head's slice of the gathered row
+    M, D = heads, C // heads
+    off = m.sampling_offsets(query).view(bs, 21, M, 4, 4, 2)
+    w = m.attention_weights(query).view(bs, 21, M, 16).softmax(-1).view(bs, 21, M, 4, 4)
+    loc = m.sampling_locations(ref_pts, off, shapes.cuda()).contiguous()
+    qt = m._query_table(21, query.device)
+    gth, ssum = cabi.msda_forward_raw(table.view(bs, cams, S, C), shapes.int().cuda(), start.int().cuda(), loc, w, qt)
+    for h in range(M):
+        lh = loc[:, :, h:h + 1].expand(-1, -1, M, -1, -1, -1).contiguous()     # every head samples like head h
+        wh = w[:, :, h:h + 1].expand(-1, -1, M, -1, -1).contiguous()
+        ref = cabi.msda_forward(table.view(bs, cams, S, M, D), shapes.int().cuda(), start.int().cuda(), lh, wh, qt)
+        assert_close(gth[:, :, h], ref, RTOL_F32, "gathered rows, head %d" % h)
+        ones = cabi.msda_forward(torch.ones_like(table).view(bs, cams, S, M, D), shapes.int().cuda(),
+                                 start.int().cuda(), lh, wh, qt)
+        assert_close(ssum[:, :, h], ones[..., 0], RTOL_F32, "weight sums, head %d" % h)
