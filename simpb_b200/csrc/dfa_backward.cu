@@ -181,7 +181,8 @@ __host__ __device__ inline MergeBwdLayout merge_bwd_layout(int P, int K, int L, 
   MergeBwdLayout s;
   s.m = merge_layout(P, K, L, G, NW, U);
   uint32_t o = s.m.total;
-  s.dot = o, o = align_up(o + 4u * G * NW * MERGE_CAP, 128);
+  s.dot = s.m.coef;  // D[slot][g] overwrites coef[slot][g]: the warp that gathers a row is the only reader of
+                     // its coefficients, and reads them (scatter) before it stores the dot products
   s.refslot = o, o = align_up(o + 8u * NW * 16u, 16);  // 4 x uint16 per tap, 16 taps per warp and round
   s.item = o, o = align_up(o + 4u * NW * 2u, 16);
   s.gl = o, o = align_up(o + 8u * P * K * L, 16);
@@ -335,8 +336,9 @@ __global__ void __launch_bounds__(NW * 32, MINB)
   uint32_t *s_table = reinterpret_cast<uint32_t *>(smem + lay.table) + warp * MERGE_TABLE;
   uint32_t *my_rowoff = s_rowoff + warp * MERGE_CAP;
   float *my_coef = s_coef + warp * MERGE_CAP * G;
-  uint32_t *s_mine_off = reinterpret_cast<uint32_t *>(smem + lay.mine_off) + warp * lay.mine_stride;
-  uint16_t *s_mine_slot = reinterpret_cast<uint16_t *>(smem + lay.mine_slot) + warp * lay.mine_stride;
+  static_assert(6 * (MERGE_CAP + U) <= 4 * MERGE_TABLE, "a warp's share lists fit its row -> slot table");
+  uint32_t *s_mine_off = reinterpret_cast<uint32_t *>(smem + lay.mine_off) + warp * MERGE_TABLE;
+  uint16_t *s_mine_slot = reinterpret_cast<uint16_t *>(smem + lay.mine_slot + 4u * warp * MERGE_TABLE);
   bool wready = !TMA;
   int li = 0, cj = 0;
 

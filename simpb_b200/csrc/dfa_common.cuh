@@ -326,9 +326,11 @@ __host__ __device__ inline MergeLayout merge_layout(int P, int K, int L, int G, 
   s.coef = o, o = align_up(o + 4u * G * slots, 128);  // reused for the NW partial rows
   s.table = o, o = align_up(o + 4u * MERGE_TABLE * NW, 128);
   s.cnt = o, o = align_up(o + 4u * NW, 16);
-  s.mine_stride = MERGE_CAP + U;  // entries per warp (a warp's share of NW lists, padded to U)
-  s.mine_off = o, o = align_up(o + 4u * s.mine_stride * NW, 16);
-  s.mine_slot = o, o = align_up(o + 2u * s.mine_stride * NW, 16);
+  // A warp's share of the NW lists (MERGE_CAP + U entries: offsets, then 16-bit slots) lives in the warp's
+  // own row -> slot table: the table is dead once the merge is done and is re-initialised by the next
+  // round's merge.  6 bytes x (MERGE_CAP + U) <= 4 bytes x MERGE_TABLE.
+  s.mine_stride = MERGE_CAP + U;
+  s.mine_off = s.table, s.mine_slot = s.table + 4u * s.mine_stride;
   s.bar = o, o += 32;
   s.total = o;
   return s;
