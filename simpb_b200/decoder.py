@@ -468,8 +468,12 @@ class SimPBFrame(nn.Module):
     """models/simpb.py:63-122 at inference: images [bs, 6, 3, 256, 704] -> ResNet-50 + FPN under fp16
     autocast (auto_fp16, fp32 out) -> feature_maps_format -> head."""
 
-    def __init__(self, seed=0, static_queries=None):
+    def __init__(self, seed=0, static_queries=None, table_dtype=None):
+        """table_dtype=torch.bfloat16: the neck's pyramid is flattened straight into a bfloat16 channel-last
+        table that both gathers consume natively — half the bytes per gathered row; the
+        reference's table is fp32 (auto_fp16(out_fp32=True)), so this is an optional mode."""
         super().__init__()
+        self.table_dtype = table_dtype
         import torchvision
         torch.manual_seed(seed)
         r = torchvision.models.resnet50(weights=None)
@@ -505,7 +509,7 @@ class SimPBFrame(nn.Module):
                 x = s(x)
                 feats.append(x)
             maps = self.neck(feats)
-        return feature_maps_format([m.float().reshape(bs, K, *m.shape[1:]) for m in maps])
+        return feature_maps_format([m.float().reshape(bs, K, *m.shape[1:]) for m in maps], dtype=self.table_dtype)
 
     def forward(self, img, metas):
         return self.head(self.extract_feat(img), metas)

@@ -87,3 +87,23 @@ def test_folded_batchnorm_is_the_same_backbone():
         out = m.fold_batchnorm().extract_feat(img)[0]
     assert not any(isinstance(x, torch.nn.BatchNorm2d) for x in m.modules())
     assert float((out - ref).abs().max() / ref.abs().max()) < 2e-2      # fp16 autocast on both sides
+
+
+@pytest.mark.gpu
+def test_bfloat16_table_from_the_neck():
+    """the frame with the pyramid flattened into a bfloat16 table — both gathers (fused DFA
+    forward, MSDA on the unprojected table) read it natively.  First frame against the fp32-table frame."""
+    from simpb_b200 import decoder, synthetic
+    proj, wh = synthetic.camera_rig(1)
+    metas = dict(projection_mat=proj.cuda(), image_wh=wh.cuda(), img_wh=(704.0, 256.0))
+    img = torch.randn(1, 6, 3, 256, 704, generator=torch.Generator().manual_seed(7)).cuda()
+    outs = []
+    for dt in (None, torch.bfloat16):
+        m = decoder.SimPBFrame(seed=3, static_queries=320, table_dtype=dt).cuda().eval()
+        with torch.no_grad():
+            fm = m.extract_feat(img)
+            assert fm[0].dtype == (torch.float32 if dt is None else torch.bfloat16)
+            outs.append(m.head(fm, metas))
+    (a0, c0, _), (a1, c1, _) = outs
+    assert float((a0 - a1).abs().max() / a0.abs().max()) < 2e-2
+    assert float((c0 - c1).abs().max() / c0.abs().max()) < 2e-2
