@@ -468,7 +468,7 @@ class SimPBFrame(nn.Module):
     """models/simpb.py:63-122 at inference: images [bs, 6, 3, 256, 704] -> ResNet-50 + FPN under fp16
     autocast (auto_fp16, fp32 out) -> feature_maps_format -> head."""
 
-    def __init__(self, seed=0, static_queries=None, table_dtype=None):
+    def __init__(self, seed=0, static_queries=None, table_dtype=None, backbone="resnet50"):
         """table_dtype=torch.bfloat16: the neck's pyramid is flattened straight into a bfloat16 channel-last
         table that both gathers consume natively — half the bytes per gathered row; the
         reference's table is fp32 (auto_fp16(out_fp32=True)), so this is an optional mode."""
@@ -476,7 +476,9 @@ class SimPBFrame(nn.Module):
         self.table_dtype = table_dtype
         import torchvision
         torch.manual_seed(seed)
-        r = torchvision.models.resnet50(weights=None)
+        # resnet50 (released config) or resnet101.  There is no checkpoint here; zero-initialised last BatchNorm
+        # scales keep the fp16 activations of a RANDOM network finite (same kernels, same cost)
+        r = getattr(torchvision.models, backbone)(weights=None, zero_init_residual=True)
         self.stem = nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool)
         self.stages = nn.ModuleList([r.layer1, r.layer2, r.layer3, r.layer4])
         self.neck = FPN()

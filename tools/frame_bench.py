@@ -77,27 +77,34 @@ def run(frames=12, warmup=4, seed=0, breakdown=True):
     return rec
 
 
-def run_graph(frames=30, warmup=4, seed=0, cap=320, fold_bn=False, tf32=False):
+CONFIGS = {   # backbone, image (H, W), rig scale / crop of synthetic.camera_rig
+    "r50": ("resnet50", (256, 704), dict(scale=0.44, crop_h=140.0, image_wh=(704.0, 256.0))),
+    "r101": ("resnet101", (512, 1408), dict(scale=0.88, crop_h=280.0, image_wh=(1408.0, 512.0))),   # BASELINE config #4
+}
+
+
+def run_graph(frames=30, warmup=4, seed=0, cap=320, fold_bn=False, tf32=False, config="r50", batch=1):
     """The whole frame as ONE CUDA graph (static 2-D query slots).  Per frame: H2D copy of the six images
     from pinned memory + the ego-motion inputs, one graph replay, D2H of the classification scores.
     fold_bn: BatchNorm folded into the convolutions (deployment transform).  tf32: fp32 matrix products of
     the decoder's nn.Linear / attention projections on the tensor cores (torch's allow_tf32; NOT the
     reference's arithmetic — reported separately)."""
     dev = "cuda"
-    model = decoder.SimPBFrame(seed=seed, static_queries=cap).to(dev).eval()
+    backbone, (ih, iw), rig = CONFIGS[config]
+    model = decoder.SimPBFrame(seed=seed, static_queries=cap, backbone=backbone).to(dev).eval()
     if fold_bn:
         model.fold_batchnorm()
     old_tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
-    proj, wh = synthetic.camera_rig(1)
+    proj, wh = synthetic.camera_rig(batch, **rig)
     gen = torch.Generator().manual_seed(seed)
-    host_imgs = [torch.randn(1, 6, 3, 256, 704, generator=gen).pin_memory() for _ in range(3)]
-    img = torch.empty(1, 6, 3, 256, 704, device=dev)
-    T = torch.eye(4)[None].clone()
-    T[0, 1, 3] = -2.5                       # previous ego frame -> current: 2.5 m behind
-    metas = dict(projection_mat=proj.to(dev), image_wh=wh.to(dev), img_wh=(704.0, 256.0),
-                 T_temp2cur=T.to(dev), dt=torch.full((1,), 0.5, device=dev))
-    host_cls = torch.empty(1, 900, 10).pin_memory()
+    host_imgs = [torch.randn(batch, 6, 3, ih, iw, generator=gen).pin_memory() for _ in range(3)]
+    img = torch.empty(batch, 6, 3, ih, iw, device=dev)
+    T = torch.eye(4)[None].repeat(batch, 1, 1)
+    T[:, 1, 3] = -2.5                       # previous ego frame -> current: 2.5 m behind
+    metas = dict(projection_mat=proj.to(dev), image_wh=wh.to(dev), img_wh=rig["image_wh"],
+                 T_temp2cur=T.to(dev), dt=torch.full((batch,), 0.5, device=dev))
+    host_cls = torch.empty(batch, 900, 10).pin_memory()
     stream = torch.cuda.Stream()
     with torch.no_grad(), torch.cuda.stream(stream):
         for i in range(3):                  # eager warm-up: creates the bank's (static) cache buffers
@@ -122,12 +129,14 @@ def run_graph(frames=30, warmup=4, seed=0, cap=320, fold_bn=False, tf32=False):
     ms = statistics.median(times)
     torch.backends.cuda.matmul.allow_tf32 = old_tf32
     assert torch.isfinite(host_cls).all()
-    return {"workload": "same frame as ONE CUDA-graph replay: %d static 2-D query slots per camera (%d queries), "
-                        "images copied from pinned host memory and class scores copied back inside the frame%s%s"
-                        % (cap, 6 * cap, "; BatchNorm folded into the convolutions" if fold_bn else "",
+    return {"workload": "%s %dx%d frame(s), bs=%d, as ONE CUDA-graph replay: %d static 2-D query slots per camera "
+                        "(%d queries), images copied from pinned host memory and class scores copied back inside "
+                        "the timed step%s%s"
+                        % (backbone, iw, ih, batch, cap, 6 * cap,
+                           "; BatchNorm folded into the convolutions" if fold_bn else "",
                            "; fp32 matrix products in TF32 (not the reference's arithmetic)" if tf32 else ""),
-            "frames_per_sec": 1e3 / ms, "ms_per_frame": ms, "frames_timed": frames, "warmup_frames": warmup,
-            "h2d_bytes_per_frame": img.numel() * 4, "d2h_bytes_per_frame": host_cls.numel() * 4}
+            "frames_per_sec": batch * 1e3 / ms, "ms_per_frame": ms / batch, "ms_per_step": ms, "batch": batch, "frames_timed": frames, "warmup_frames": warmup,
+            "h2d_bytes_per_step": img.numel() * 4, "d2h_bytes_per_step": host_cls.numel() * 4}
 
 
 if __name__ == "__main__":
@@ -136,8 +145,14 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--mode", default="both", choices=["eager", "graph", "both"])
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--config", default="r50", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=1)
     a = ap.parse_args()
     rec = {}
+    if a.config != "r50" or a.batch != 1:     # BASELINE config #4: graph mode only
+        rec["graph"] = run_graph(max(a.frames, 12), a.warmup, config=a.config, batch=a.batch)
+        print(json.dumps(rec))
+        sys.exit(0)
     if a.mode in ("eager", "both"):
         rec["eager"] = run(a.frames, a.warmup, breakdown=not a.no_breakdown)
     if a.mode in ("graph", "both"):
